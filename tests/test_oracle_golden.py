@@ -1,0 +1,93 @@
+"""CPU: the oracle restatement (oracle/cer_oracle.py) against golden outputs of the reference's own
+Python (tests/golden/*.npz, made by oracle/gen_golden.py from /root/reference)."""
+import numpy as np
+import torch
+
+import cer_oracle as O
+from cer_mvs_b200 import synth
+from conftest import rel_l1
+
+H, W, V = 80, 112, 3
+h1, w1 = H // 4, W // 4
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _scene(seed):
+    sc = synth.make_scene(H, W, V, seed=seed)
+    K = t(sc["intrinsics"]).clone()
+    K[:, :, :2] /= 4
+    return t(sc["fmaps"]), t(sc["poses"]), K, sc
+
+
+def test_projective_transform(golden):
+    g = golden("ops_corrblock")
+    fm, poses, K, _ = _scene(1)
+    Pij = O.projection_matrices(poses, K, [0], [2])
+    x = O.project_hypotheses(Pij, t(g["proj_disps"]))              # [1,1,h,w,D,2]
+    ref = t(g["proj_x1"])[..., [0, 1]].permute(0, 1, 3, 4, 2, 5)
+    assert torch.allclose(x, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_build_volume_and_pyramid(golden):
+    g = golden("ops_corrblock")
+    fm, poses, K, _ = _scene(1)
+    for stage, (D, incre, shift) in enumerate([(64, 0.0025 / 64, True), (44, 0.0025 / 320, False)]):
+        pyr, origin = O.build_volume(fm, poses, K, [0] * V, [1, 2, 3], D, incre,
+                                     t(g[f"s{stage}_disp_in"]), shift)
+        assert np.array_equal(origin.numpy(), g[f"s{stage}_origin"])
+        for l in range(3):
+            got = pyr[l].reshape(V * h1 * w1, -1).numpy()
+            assert got.shape == g[f"s{stage}_pyr{l}"].shape
+            np.testing.assert_allclose(got, g[f"s{stage}_pyr{l}"], rtol=1e-5, atol=1e-6)
+
+
+def test_lookup(golden):
+    g = golden("ops_corrblock")
+    for stage, (D, incre) in enumerate([(64, 0.0025 / 64), (44, 0.0025 / 320)]):
+        pyr = [t(g[f"s{stage}_pyr{l}"]).reshape(-1, 1, 1, g[f"s{stage}_pyr{l}"].shape[-1]) for l in range(3)]
+        origin = t(g[f"s{stage}_origin"])
+        for name in ("true", "zero", "far", "rand"):
+            z = t(g[f"s{stage}_z_{name}"])
+            out = O.lookup(pyr, origin, D, incre, z[:, [0] * V], radius=5)
+            np.testing.assert_allclose(out.numpy(), g[f"s{stage}_lookup_{name}"], rtol=1e-5, atol=2e-6)
+
+
+def test_update_block(golden):
+    g = golden("ops_update")
+    sd = O.to_torch_sd(synth.make_update_weights(seed=2, delta_scale=1.0))
+    np.testing.assert_array_equal(O.disp_encoder(t(g["disp"])).numpy(), g["disp_enc"])
+    for stage in (0, 1):
+        net, delta = O.update_block(sd, t(g["net"]), t(g["inp"]), t(g["disp"]), t(g["corr_frames"]), stage)
+        np.testing.assert_allclose(net.numpy(), g[f"net_out{stage}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(delta.numpy(), g[f"delta{stage}"], rtol=1e-4, atol=1e-7)
+
+
+def _e2e(golden, name, autocast):
+    g = golden(name)
+    seed = int(g["seed"])
+    sc = synth.make_scene(H, W, V, seed=seed)
+    sd = O.to_torch_sd(synth.make_update_weights(seed=seed, delta_scale=float(g["delta_scale"]),
+                                                 delta_bias=float(g["delta_bias"]) if "delta_bias" in g else 0.0))
+    cascade = [tuple(int(v) for v in row) for row in g["cascade"]]
+    out, trace = O.hot_path(sd, t(sc["fmaps"]), t(g["net"]), t(g["inp"]), t(sc["poses"]), t(sc["intrinsics"]),
+                            cascade=cascade, scale=float(g["scale"]), autocast=autocast, return_all=True)
+    return out.numpy(), g["disp"], trace, g["deltas"]
+
+
+def test_e2e_fp32(golden):
+    for name in ("trained_like", "unscaled_oob", "drift", "scaled_pose"):
+        out, ref, trace, deltas = _e2e(golden, "e2e_fp32_" + name, autocast=False)
+        assert ref.dtype == np.float64 and out.shape == ref.shape      # core/raft.py:108 -> float64
+        err = rel_l1(out, ref)
+        assert err < 1e-4, (name, err)
+
+
+def test_e2e_autocast_emulation(golden):
+    """The fp16-rounding emulation against the reference run under torch.autocast('cpu', float16)
+    (proxy for the GPU autocast path, core/raft.py:55)."""
+    out, ref, _, _ = _e2e(golden, "e2e_autocast_drift", autocast=True)
+    err = rel_l1(out, ref)
+    assert err < 1e-3, err
