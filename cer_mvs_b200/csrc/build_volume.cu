@@ -1,0 +1,177 @@
+// Fused epipolar cost-volume build: CorrBlock.__init__ of the reference (core/corr.py:46-97) in
+// one kernel -- hypotheses, projection, clamp, bilinear gather, 64-channel dot, view sum, D-minor
+// layout.  No coords tensor, no per-view transposes, no global read-modify-write.
+//
+// Mapping: an 8-lane group owns one reference pixel.  Lane L of the group computes the epipolar
+// sample position of hypothesis d0+L (so the projective arithmetic is done once per sample, not
+// once per lane), the group then walks the 8 samples: every lane reads its 8-channel slice
+// (16 B fp16 / 32 B fp32) of the four corner pixels -- a warp instruction touches 4 source pixels
+// = 4 full 128-byte lines (fp16) -- and accumulates slice dots weighted by the bilinear weights.
+// A 7-shuffle butterfly leaves the full dot of sample d0+L in lane L, which adds it to its
+// view-sum accumulator and finally stores 8 consecutive hypotheses (32 B) per group.
+#include "common.cuh"
+
+namespace cer {
+
+constexpr int kMaxPairs = 64;
+constexpr int kChunksPerBlock = 2;  // hypothesis chunks (of 8) handled by one block in sequence
+
+template <typename T>
+struct FeatSlice;  // 8 channels of one pixel
+
+template <>
+struct FeatSlice<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&f)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+};
+
+template <>
+struct FeatSlice<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) build_volume_kernel(
+    const T* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
+    const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
+    float lo_origin, float* __restrict__ origin_out, float* __restrict__ volume, float out_scale, int per_view,
+    int h, int w) {
+  __shared__ float sP[kMaxPairs][12];
+  __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
+  for (int t = threadIdx.x; t < n_pairs * 12; t += blockDim.x) sP[t / 12][t % 12] = Pij[(t / 12) * 16 + (t % 12)];
+  for (int t = threadIdx.x; t < n_pairs; t += blockDim.x) {
+    sI[t] = ii[t];
+    sJ[t] = jj[t];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 7;
+  const long long px = (long long)h * w;
+  const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool valid = pix < px;
+  const long long p = valid ? pix : px - 1;
+  const int x = (int)(p % w), y = (int)(p / w);
+  const float xf = (float)x, yf = (float)y;
+
+  // hypothesis origin (core/corr.py:59-63)
+  const float din = __ldg(disp_in + p);
+  const float org = shift ? (din < lo_origin ? lo_origin : din) : din;
+  if (valid && lane == 0 && blockIdx.y == 0) origin_out[p] = org;
+
+  const long long img_stride = px * kFeatC;
+  int cached_ref = -1;
+  float f1[8];
+
+  const int chunk0 = blockIdx.y * kChunksPerBlock;
+  for (int ch = chunk0; ch < chunk0 + kChunksPerBlock; ++ch) {
+    const int d0 = ch * 8;
+    if (d0 >= D) break;
+    const int d = d0 + lane;
+    // d_k = origin + (k - D//2) * incre, rounded like the reference's two tensor ops (corr.py:56,66)
+    const float dval = __fadd_rn(__fmul_rn((float)(min(d, D - 1) - D / 2), incre), org);
+    float acc = 0.f;
+    for (int k = 0; k < n_pairs; ++k) {
+      const int ri = sI[k];
+      if (ri != cached_ref) {  // block-uniform
+        FeatSlice<T>::load(feats + ri * img_stride + p * kFeatC + lane * 8, f1);
+        cached_ref = ri;
+      }
+      const T* img2 = feats + sJ[k] * img_stride + lane * 8;
+      const float* P = sP[k];
+      // X = Pij . (x, y, 1, d)   (utils/projective_ops.py:25-27), then /X2 and clamp (corr.py:88)
+      const float X0 = fmaf(P[3], dval, fmaf(P[1], yf, P[0] * xf) + P[2]);
+      const float X1 = fmaf(P[7], dval, fmaf(P[5], yf, P[4] * xf) + P[6]);
+      const float X2 = fmaf(P[11], dval, fmaf(P[9], yf, P[8] * xf) + P[10]);
+      float u = __fdiv_rn(X0, X2), v = __fdiv_rn(X1, X2);
+      u = u < -1e4f ? -1e4f : (u > 1e4f ? 1e4f : u);  // NaN-preserving clamp
+      v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
+      const float fu = floorf(u), fv = floorf(v);
+      const float my_dx = u - fu, my_dy = v - fv;
+      const int my_ix = (int)fu, my_iy = (int)fv;
+
+      float part[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int ix = __shfl_sync(0xffffffffu, my_ix, s, 8);
+        const int iy = __shfl_sync(0xffffffffu, my_iy, s, 8);
+        const float dx = __shfl_sync(0xffffffffu, my_dx, s, 8);
+        const float dy = __shfl_sync(0xffffffffu, my_dy, s, 8);
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int yy = iy + (c >> 1), xx = ix + (c & 1);
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            float f2[8];
+            FeatSlice<T>::load(img2 + ((long long)yy * w + xx) * kFeatC, f2);
+            float dot = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dot = fmaf(f1[e], f2[e], dot);
+            const float wy = (c >> 1) ? dy : 1.f - dy;
+            const float wx = (c & 1) ? dx : 1.f - dx;
+            sum += (dot * wy) * wx;
+          } else if (dx != dx || dy != dy) {
+            sum = dx + dy;  // NaN coordinates poison the output like the reference (0 * NaN)
+          }
+        }
+        part[s] = sum;
+      }
+      // butterfly: lane L ends with the group-wide total of sample L
+      float k4[4], k2[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = (lane & 4) ? part[i] : part[i + 4];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        k4[i] = ((lane & 4) ? part[i + 4] : part[i]) + recv;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = (lane & 2) ? k4[i] : k4[i + 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        k2[i] = ((lane & 2) ? k4[i + 2] : k4[i]) + recv;
+      }
+      const float send = (lane & 1) ? k2[0] : k2[1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      const float total = ((lane & 1) ? k2[1] : k2[0]) + recv;
+      if (per_view) {
+        if (valid && d < D) volume[((long long)k * px + p) * D + d] = total * out_scale;
+      } else {
+        acc += total;
+      }
+    }
+    if (!per_view && valid && d < D) volume[p * D + d] = acc * out_scale;
+  }
+}
+
+}  // namespace cer
+
+using namespace cer;
+
+extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+                                int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
+                                float* origin, float* volume, float out_scale, int per_view, int h, int w,
+                                cer_stream_t stream) {
+  CER_REQUIRE(feats && Pij && ii && jj && disp_in && origin && volume, "cer_build_volume: null pointer");
+  CER_REQUIRE(n_pairs > 0 && n_pairs <= kMaxPairs, "cer_build_volume: n_pairs must be 1..%d", kMaxPairs);
+  CER_REQUIRE(D > 0 && h > 0 && w > 0, "cer_build_volume: bad sizes");
+  CER_REQUIRE(aligned16(feats), "cer_build_volume: feats must be 16-byte aligned");
+  const long long px = (long long)h * w;
+  const int chunks = ceil_div(D, 8);
+  dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
+  if (feats_f16)
+    CER_LAUNCH(build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
+               shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+  else
+    CER_LAUNCH(build_volume_kernel<float>, grid, 256, 0, stream, (const float*)feats, Pij, ii, jj, n_pairs, disp_in,
+               shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+  return check_launch("cer_build_volume");
+}

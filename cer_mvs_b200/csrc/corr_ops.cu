@@ -1,0 +1,430 @@
+// Correlation-side small kernels: error plumbing, the alt_cuda_corr.forward drop-in, layout
+// changes, projection matrices, pyramid pooling and the fused pyramid lookup.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cer {
+
+static thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  return CER_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// alt_cuda_corr.forward drop-in.  One 8-lane group per (b, n, y, x) sample; lanes stride over the
+// channel dimension (float4 when C % 4 == 0), 3 xor-shuffles reduce the dot products.
+// Restates correlation_kernel.cu:59-116: output (oy, ox) of the (2r+1)^2 window is the bilinear
+// blend of the dots at integer pixels (fy-r+oy+{0,1}, fx-r+ox+{0,1}); index oy + rd*ox.
+// ------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256) corr_forward_dropin_kernel(
+    const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ coords,
+    float* __restrict__ corr, int B, int H1, int W1, int H2, int W2, int C, int N, int r) {
+  const long long total = (long long)B * N * H1 * W1;
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int lane = threadIdx.x & 7;
+  const bool valid = gid < total;
+  const long long g = valid ? gid : total - 1;
+  const int x = (int)(g % W1);
+  const int y = (int)((g / W1) % H1);
+  const int n = (int)((g / ((long long)W1 * H1)) % N);
+  const int b = (int)(g / ((long long)W1 * H1 * N));
+  const float cx = __ldg(coords + 2 * g);
+  const float cy = __ldg(coords + 2 * g + 1);
+  const float fxf = floorf(cx), fyf = floorf(cy);
+  const float dx = cx - fxf, dy = cy - fyf;
+  const int fx = (int)fxf, fy = (int)fyf;  // NaN -> 0 like the reference's cvt
+  const float* p1 = f1 + (((long long)b * H1 + y) * W1 + x) * C;
+  const float* img2 = f2 + (long long)b * H2 * W2 * C;
+  const int rd = 2 * r + 1;
+  const long long plane = (long long)H1 * W1;
+  float* out = corr + (((long long)b * N + n) * rd * rd) * plane + (long long)y * W1 + x;
+  for (int ox = 0; ox < rd; ++ox) {
+    for (int oy = 0; oy < rd; ++oy) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int h2 = fy - r + oy + (k >> 1);
+        const int w2 = fx - r + ox + (k & 1);
+        float s = 0.f;
+        if (h2 >= 0 && h2 < H2 && w2 >= 0 && w2 < W2) {
+          const float* p2 = img2 + ((long long)h2 * W2 + w2) * C;
+          if (VEC4) {
+            for (int c = lane * 4; c < C; c += 32) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p1 + c));
+              const float4 q = __ldg(reinterpret_cast<const float4*>(p2 + c));
+              s = fmaf(a.x, q.x, s);
+              s = fmaf(a.y, q.y, s);
+              s = fmaf(a.z, q.z, s);
+              s = fmaf(a.w, q.w, s);
+            }
+          } else {
+            for (int c = lane; c < C; c += 8) s = fmaf(__ldg(p1 + c), __ldg(p2 + c), s);
+          }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        acc += (s * ((k >> 1) ? dy : 1.f - dy)) * ((k & 1) ? dx : 1.f - dx);   // s*(1-dy)*(1-dx) etc., kernel.cu:97-100
+      }
+      if (valid && lane == 0) out[(long long)(oy + rd * ox) * plane] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW <-> NHWC with dtype change and scale.  Tile = 64 channels x 32 pixels through smem.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TS* __restrict__ src, TD* __restrict__ dst,
+                                                          int C, int dstC, long long px, float scale) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const TS* s = src + (long long)n * C * px;
+  TD* d = dst + (long long)n * dstC * px;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    const long long p = p0 + tx;
+    tile[ty + 8 * k][tx] = (c < C && p < px) ? to_f<TS>(s[(long long)c * px + p]) * scale : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long p = p0 + ty + 8 * k;
+    const int c = c0 + tx;
+    if (c < dstC && p < px) d[p * dstC + c] = from_f<TD>(tile[tx][ty + 8 * k]);   // channels C..dstC-1 are zero
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const TS* __restrict__ src, TD* __restrict__ dst,
+                                                          int C, long long px) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const TS* s = src + (long long)n * C * px;
+  TD* d = dst + (long long)n * C * px;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long p = p0 + ty + 8 * k;
+    const int c = c0 + tx;
+    tile[ty + 8 * k][tx] = (c < C && p < px) ? to_f<TS>(s[p * C + c]) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    const long long p = p0 + tx;
+    if (c < C && p < px) d[(long long)c * px + p] = from_f<TD>(tile[tx][ty + 8 * k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pij = K4_j P_j P_i^-1 K4_i^-1 in fp64 (one thread per pair), utils/projective_ops.py:16-23
+// ------------------------------------------------------------------------------------------
+__device__ void mat4_mul(const double* a, const double* b, double* c) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+      c[i * 4 + j] = s;
+    }
+}
+
+__device__ void mat4_inv(const double* m, double* inv) {  // Gauss-Jordan, partial pivoting
+  double a[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      a[i][j] = m[i * 4 + j];
+      a[i][4 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (piv != c)
+      for (int j = 0; j < 8; ++j) {
+        double t = a[c][j];
+        a[c][j] = a[piv][j];
+        a[piv][j] = t;
+      }
+    const double d = 1.0 / a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] *= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const double f = a[r][c];
+        for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) inv[i * 4 + j] = a[i][4 + j];
+}
+
+__global__ void projection_matrices_kernel(const float* __restrict__ poses, const float* __restrict__ K,
+                                           const int* __restrict__ ii, const int* __restrict__ jj,
+                                           int n_pairs, float* __restrict__ Pij) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_pairs) return;
+  const int i = ii[k], j = jj[k];
+  double Ki[16], Kj[16], Pi[16], Pj[16], t0[16], t1[16], t2[16];
+  for (int a = 0; a < 16; ++a) {
+    Ki[a] = Kj[a] = 0.0;
+    Pi[a] = poses[i * 16 + a];
+    Pj[a] = poses[j * 16 + a];
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      Ki[r * 4 + c] = K[i * 9 + r * 3 + c];
+      Kj[r * 4 + c] = K[j * 9 + r * 3 + c];
+    }
+  Ki[15] = Kj[15] = 1.0;
+  mat4_mul(Kj, Pj, t0);
+  mat4_inv(Pi, t1);
+  mat4_mul(t0, t1, t2);
+  mat4_inv(Ki, t1);
+  mat4_mul(t2, t1, t0);
+  for (int a = 0; a < 16; ++a) Pij[k * 16 + a] = (float)t0[a];
+}
+
+// ------------------------------------------------------------------------------------------
+// avg_pool2d([1,2]) (core/corr.py:96)
+// ------------------------------------------------------------------------------------------
+__global__ void pool_pairs_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int W) {
+  const int Wo = W / 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Wo) return;
+  const long long r = idx / Wo;
+  const int c = (int)(idx % Wo);
+  dst[idx] = (src[r * W + 2 * c] + src[r * W + 2 * c + 1]) * 0.5f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused pyramid lookup (core/corr.py:102-143).  Block = 128 pixels of one slot: the level-0 rows are
+// staged in shared memory with coalesced 16-byte loads (4*D bytes per pixel is the only volume read),
+// levels 1..2 are rebuilt from it on the fly, each thread produces the L*(2r+1) taps of its pixel.
+// ------------------------------------------------------------------------------------------
+constexpr int kLookupPix = 128;
+
+__device__ __forceinline__ float pyr_value(const float* row, int lvl, int i, int D) {
+  // value i of pyramid level lvl (floor pooling); caller guarantees 0 <= i < (D >> lvl)
+  if (lvl == 0) return row[i];
+  if (lvl == 1) return (row[2 * i] + row[2 * i + 1]) * 0.5f;
+  const float a = (row[4 * i] + row[4 * i + 1]) * 0.5f;
+  const float b = (row[4 * i + 2] + row[4 * i + 3]) * 0.5f;
+  return (a + b) * 0.5f;
+}
+
+__global__ void __launch_bounds__(kLookupPix) lookup_kernel(
+    const float* __restrict__ volume, const float* __restrict__ origin, const float* __restrict__ zinv,
+    long long zinv_stride, int D, float incre, int radius, int num_levels, float* __restrict__ out,
+    long long px) {
+  extern __shared__ float rows[];  // [kLookupPix][D + 1]
+  const int slot = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * kLookupPix;
+  const int npix = (int)min((long long)kLookupPix, px - p0);
+  const float* vsrc = volume + ((long long)slot * px + p0) * D;
+  const int pitch = D + 1;
+  if ((D & 3) == 0) {
+    const int nvec = npix * D / 4;
+    for (int i = threadIdx.x; i < nvec; i += kLookupPix) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(vsrc) + i);
+      const int e = i * 4;
+      const int r = e / D, c = e % D;
+      float* d = rows + r * pitch + c;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < npix * D; i += kLookupPix) rows[(i / D) * pitch + (i % D)] = __ldg(vsrc + i);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= npix) return;
+  const long long p = p0 + threadIdx.x;
+  const float* row = rows + threadIdx.x * pitch;
+  const float z = __ldg(zinv + slot * zinv_stride + p);
+  const float o = __ldg(origin + p);
+  // coords = max((zinv - origin) / incre + D//2, 0)   (core/corr.py:107)
+  const float c = fmaxf(__fadd_rn(__fdiv_rn(__fsub_rn(z, o), incre), (float)(D / 2)), 0.f);
+  const int taps = 2 * radius + 1;
+  float* o_ptr = out + (long long)slot * num_levels * taps * px + p;
+  for (int lvl = 0; lvl < num_levels; ++lvl) {
+    const int Wl = D >> lvl;
+    const float cl = c / (float)(1 << lvl);
+    const float wm1 = (float)(Wl - 1);
+    for (int j = -radius; j <= radius; ++j) {
+      const float x0 = __fadd_rn((float)j, cl);                                   // corr.py:129
+      const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, x0), wm1), 1.f);        // bilinear_sampler.py:12
+      const float xp = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), wm1);        // grid_sample unnormalize
+      const float fl = floorf(xp);
+      const float w1 = xp - fl;
+      const float w0 = (fl + 1.f) - xp;
+      float v = 0.f;
+      // zero padding: taps outside [0, Wl) contribute nothing; huge |xp| is out on both sides
+      if (fl >= -1.f && fl < (float)Wl) {
+        const int i0 = (int)fl;
+        const float v0 = (i0 >= 0) ? pyr_value(row, lvl, i0, D) : 0.f;
+        const float v1 = (i0 + 1 < Wl) ? pyr_value(row, lvl, i0 + 1, D) : 0.f;
+        v = v0 * w0 + v1 * w1;
+      }
+      o_ptr[(long long)(lvl * taps + (j + radius)) * px] = v;
+    }
+  }
+}
+
+}  // namespace cer
+
+using namespace cer;
+
+extern "C" {
+
+int cer_abi_version(void) { return 1; }
+const char* cer_last_error(void) { return cer::g_err; }
+
+int cer_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device: %s (cer_mvs_b200 has no CPU fallback)", cudaGetErrorString(e));
+    return CER_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  CER_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    return CER_ERR_NO_DEVICE;
+  }
+  return CER_OK;
+}
+
+int cer_corr_forward_f32(const float* fmap1, const float* fmap2, const float* coords, float* corr, int B,
+                         int H1, int W1, int H2, int W2, int C, int N, int radius, cer_stream_t stream) {
+  CER_REQUIRE(fmap1 && fmap2 && coords && corr, "cer_corr_forward_f32: null pointer");
+  CER_REQUIRE(B >= 0 && H1 >= 0 && W1 >= 0 && H2 > 0 && W2 > 0 && C > 0 && N >= 0 && radius >= 0,
+              "cer_corr_forward_f32: bad sizes");
+  const long long total = (long long)B * N * H1 * W1;
+  if (total == 0) return CER_OK;
+  const long long threads = total * 8;
+  CER_REQUIRE(threads / 256 < 0x7fffffffLL, "cer_corr_forward_f32: problem too large");
+  const bool vec = (C % 4 == 0) && aligned16(fmap1) && aligned16(fmap2);
+  const int grid = ceil_div(threads, 256);
+  if (vec)
+    CER_LAUNCH(corr_forward_dropin_kernel<true>, grid, 256, 0, stream, fmap1, fmap2, coords, corr, B, H1, W1, H2,
+               W2, C, N, radius);
+  else
+    CER_LAUNCH(corr_forward_dropin_kernel<false>, grid, 256, 0, stream, fmap1, fmap2, coords, corr, B, H1, W1, H2,
+               W2, C, N, radius);
+  return check_launch("cer_corr_forward_f32");
+}
+
+int cer_nchw_to_nhwc_pad(const void* src, int src_f16, void* dst, int dst_f16, int n, int C, int dstC, int h,
+                         int w, float scale, cer_stream_t stream) {
+  CER_REQUIRE(src && dst && n > 0 && C > 0 && dstC >= C && h > 0 && w > 0, "cer_nchw_to_nhwc: bad arguments");
+  const long long px = (long long)h * w;
+  dim3 grid(ceil_div(px, 32), ceil_div(dstC, 32), n);
+  if (src_f16 && dst_f16)
+    CER_LAUNCH((nchw_to_nhwc_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, dstC, px, scale);
+  else if (src_f16 && !dst_f16)
+    CER_LAUNCH((nchw_to_nhwc_kernel<__half, float>), grid, 256, 0, stream, (const __half*)src, (float*)dst, C, dstC, px, scale);
+  else if (!src_f16 && dst_f16)
+    CER_LAUNCH((nchw_to_nhwc_kernel<float, __half>), grid, 256, 0, stream, (const float*)src, (__half*)dst, C, dstC, px, scale);
+  else
+    CER_LAUNCH((nchw_to_nhwc_kernel<float, float>), grid, 256, 0, stream, (const float*)src, (float*)dst, C, dstC, px, scale);
+  return check_launch("cer_nchw_to_nhwc");
+}
+
+int cer_nchw_to_nhwc(const void* src, int src_f16, void* dst, int dst_f16, int n, int C, int h, int w,
+                     float scale, cer_stream_t stream) {
+  return cer_nchw_to_nhwc_pad(src, src_f16, dst, dst_f16, n, C, C, h, w, scale, stream);
+}
+
+int cer_nhwc_to_nchw(const void* src, int src_f16, void* dst, int dst_f16, int n, int C, int h, int w,
+                     cer_stream_t stream) {
+  CER_REQUIRE(src && dst && n > 0 && C > 0 && h > 0 && w > 0, "cer_nhwc_to_nchw: bad arguments");
+  const long long px = (long long)h * w;
+  dim3 grid(ceil_div(px, 32), ceil_div(C, 32), n);
+  if (src_f16 && dst_f16)
+    CER_LAUNCH((nhwc_to_nchw_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, px);
+  else if (src_f16 && !dst_f16)
+    CER_LAUNCH((nhwc_to_nchw_kernel<__half, float>), grid, 256, 0, stream, (const __half*)src, (float*)dst, C, px);
+  else if (!src_f16 && dst_f16)
+    CER_LAUNCH((nhwc_to_nchw_kernel<float, __half>), grid, 256, 0, stream, (const float*)src, (__half*)dst, C, px);
+  else
+    CER_LAUNCH((nhwc_to_nchw_kernel<float, float>), grid, 256, 0, stream, (const float*)src, (float*)dst, C, px);
+  return check_launch("cer_nhwc_to_nchw");
+}
+
+int cer_projection_matrices(const float* poses, const float* intrinsics, const int* ii, const int* jj,
+                            int n_pairs, float* Pij, cer_stream_t stream) {
+  CER_REQUIRE(poses && intrinsics && ii && jj && Pij && n_pairs > 0, "cer_projection_matrices: bad arguments");
+  CER_LAUNCH(projection_matrices_kernel, ceil_div(n_pairs, 32), 32, 0, stream, poses, intrinsics, ii, jj, n_pairs, Pij);
+  return check_launch("cer_projection_matrices");
+}
+
+int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stream_t stream) {
+  CER_REQUIRE(src && dst && rows >= 0 && W >= 2, "cer_pool_pairs: bad arguments");
+  const long long total = rows * (W / 2);
+  if (total == 0) return CER_OK;
+  CER_LAUNCH(pool_pairs_kernel, ceil_div(total, 256), 256, 0, stream, src, dst, rows, W);
+  return check_launch("cer_pool_pairs");
+}
+
+int cer_lookup_strided(const float* volume, int slots, const float* origin, const float* zinv,
+                       long long zinv_stride, int D, float incre, int radius, int num_levels, float* out, int h,
+                       int w, cer_stream_t stream) {
+  CER_REQUIRE(volume && origin && zinv && out, "cer_lookup: null pointer");
+  CER_REQUIRE(slots > 0 && h > 0 && w > 0 && radius >= 0, "cer_lookup: bad sizes");
+  CER_REQUIRE(num_levels >= 1 && num_levels <= 3, "cer_lookup: num_levels must be 1..3");
+  CER_REQUIRE((D >> (num_levels - 1)) >= 2, "cer_lookup: D too small for %d levels", num_levels);
+  CER_REQUIRE(D <= 1024, "cer_lookup: D > 1024 unsupported");
+  const long long px = (long long)h * w;
+  const size_t smem = (size_t)kLookupPix * (D + 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    CER_CUDA(cudaFuncSetAttribute(lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(px, kLookupPix), slots);
+  CER_LAUNCH(lookup_kernel, grid, kLookupPix, smem, stream, volume, origin, zinv, zinv_stride, D, incre, radius,
+             num_levels, out, px);
+  return check_launch("cer_lookup");
+}
+
+int cer_lookup(const float* volume, int slots, const float* origin, const float* zinv, int D, float incre,
+               int radius, int num_levels, float* out, int h, int w, cer_stream_t stream) {
+  return cer_lookup_strided(volume, slots, origin, zinv, 0, D, incre, radius, num_levels, out, h, w, stream);
+}
+
+}  // extern "C"

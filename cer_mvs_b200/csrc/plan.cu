@@ -1,0 +1,291 @@
+// cer_plan: the stage / iteration loop of RAFT.forward (core/raft.py:75-108) as a native object
+// that owns its device workspace, keeps every intermediate resident in HBM in the kernels' own
+// layouts (NHWC fp16 activations, D-minor fp32 volume) and replays each stage's iteration loop
+// from a CUDA graph.
+#include <vector>
+
+#include "common.cuh"
+#include "update_blob.h"
+
+namespace cer {
+int update_step_hmma(const void* blob, void* workspace, void* net, const void* inp, float* disp, const float* corr,
+                     int slots, float* delta, int apply_delta, int stage, int h, int w, cudaStream_t stream);
+int update_configure();
+
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, float s, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * s;
+}
+
+__global__ void iota_pairs_kernel(int* ii, int* jj, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    ii[i] = 0;
+    jj[i] = i + 1;
+  }
+}
+}  // namespace cer
+
+using namespace cer;
+
+struct cer_plan {
+  cer_plan_config cfg;
+  long long px = 0;
+  int Dmax = 0;
+  // device buffers
+  void* feats = nullptr;      // [(max_views+1)][px][64] fp16|fp32, pre-scaled by 1/8
+  __half* net = nullptr;      // [px][64]
+  __half* inp = nullptr;      // [px][64]
+  float* disp = nullptr;      // [px]
+  float* origin = nullptr;    // [px]
+  float* volume = nullptr;    // [px][Dmax]
+  float* corr = nullptr;      // [33][px]
+  float* Pij = nullptr;       // [max_views][16]
+  float* poses = nullptr;     // staging for run_host
+  float* intr = nullptr;
+  int *ii = nullptr, *jj = nullptr;
+  void* ws = nullptr;         // update workspace
+  void* blob = nullptr;
+  void* stage_in = nullptr;   // host-path staging of NCHW inputs
+  size_t stage_in_bytes = 0;
+  size_t total_bytes = 0;
+  // run state
+  int n_views = 0, vb = 0, ve = 0;
+  bool have_weights = false;
+  cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long graph_nodes[4] = {0, 0, 0, 0};
+  long long launches = 0;
+};
+
+static int plan_alloc(cer_plan* p, void** ptr, size_t bytes) {
+  CER_CUDA(cudaMalloc(ptr, bytes));
+  p->total_bytes += bytes;
+  return CER_OK;
+}
+
+extern "C" {
+
+int cer_plan_create(const cer_plan_config* cfg, cer_plan** out) {
+  CER_REQUIRE(cfg && out, "cer_plan_create: null pointer");
+  CER_REQUIRE(cfg->h > 0 && cfg->w > 0 && cfg->max_views > 0 && cfg->max_views <= 64, "cer_plan_create: bad sizes");
+  CER_REQUIRE(cfg->n_stages >= 1 && cfg->n_stages <= 2,
+              "cer_plan_create: 1 or 2 cascade stages supported (per-stage delta weights, core/update.py:67)");
+  int rc = cer_device_check();
+  if (rc) return rc;
+  cer_plan* p = new cer_plan();
+  p->cfg = *cfg;
+  p->px = (long long)cfg->h * cfg->w;
+  for (int s = 0; s < cfg->n_stages; ++s) {
+    if (cfg->D[s] < 4 || cfg->D[s] > 1024 || cfg->iters[s] < 0 || !(cfg->incre[s] > 0)) {
+      delete p;
+      set_error("cer_plan_create: bad stage %d parameters", s);
+      return CER_ERR_INVALID;
+    }
+    p->Dmax = cfg->D[s] > p->Dmax ? cfg->D[s] : p->Dmax;
+  }
+  const size_t fsz = cfg->feats_f16 ? 2 : 4;
+  const long long px = p->px;
+  bool ok = true;
+  ok = ok && !plan_alloc(p, &p->feats, (size_t)(cfg->max_views + 1) * px * 64 * fsz);
+  ok = ok && !plan_alloc(p, (void**)&p->net, px * 64 * 2);
+  ok = ok && !plan_alloc(p, (void**)&p->inp, px * 64 * 2);
+  ok = ok && !plan_alloc(p, (void**)&p->disp, px * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->origin, px * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->volume, px * p->Dmax * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->corr, px * kCorrPlanes * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->Pij, cfg->max_views * 16 * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->poses, (cfg->max_views + 1) * 16 * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->intr, (cfg->max_views + 1) * 9 * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->ii, cfg->max_views * 4);
+  ok = ok && !plan_alloc(p, (void**)&p->jj, cfg->max_views * 4);
+  ok = ok && !plan_alloc(p, &p->ws, cer_update_workspace_bytes(cfg->h, cfg->w));
+  ok = ok && !plan_alloc(p, &p->blob, cer_update_blob_bytes());
+  if (!ok) {
+    cer_plan_destroy(p);
+    return CER_ERR_INVALID;
+  }
+  iota_pairs_kernel<<<1, 64>>>(p->ii, p->jj, cfg->max_views);
+  rc = update_configure();
+  if (!rc) rc = (int)cudaDeviceSynchronize();
+  if (rc) {
+    cer_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return CER_OK;
+}
+
+void cer_plan_destroy(cer_plan* p) {
+  if (!p) return;
+  for (int s = 0; s < 4; ++s)
+    if (p->graph[s]) cudaGraphExecDestroy(p->graph[s]);
+  void* ptrs[] = {p->feats, p->net, p->inp, p->disp, p->origin, p->volume, p->corr, p->Pij, p->poses,
+                  p->intr,  p->ii,  p->jj,  p->ws,   p->blob,   p->stage_in};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  delete p;
+}
+
+size_t cer_plan_workspace_bytes(const cer_plan* p) { return p ? p->total_bytes + p->stage_in_bytes : 0; }
+
+int cer_plan_set_weights(cer_plan* p, const void* blob_host) {
+  CER_REQUIRE(p && blob_host, "cer_plan_set_weights: null pointer");
+  CER_CUDA(cudaMemcpy(p->blob, blob_host, cer_update_blob_bytes(), cudaMemcpyHostToDevice));
+  p->have_weights = true;
+  return CER_OK;
+}
+
+int cer_plan_prepare(cer_plan* p, const void* fmaps, int fmaps_f16, const void* net, const void* inp, int ctx_f16,
+                     const float* poses, const float* intrinsics, int n_views, int view_begin, int view_end,
+                     cer_stream_t stream) {
+  CER_REQUIRE(p && fmaps && net && inp && poses && intrinsics, "cer_plan_prepare: null pointer");
+  CER_REQUIRE(p->have_weights, "cer_plan_prepare: call cer_plan_set_weights first");
+  CER_REQUIRE(n_views >= 1 && n_views <= p->cfg.max_views, "cer_plan_prepare: n_views %d outside 1..%d", n_views,
+              p->cfg.max_views);
+  CER_REQUIRE(view_begin >= 0 && view_begin < view_end && view_end <= n_views, "cer_plan_prepare: bad view range");
+  const int h = p->cfg.h, w = p->cfg.w;
+  const long long px = p->px;
+  const size_t in_sz = fmaps_f16 ? 2 : 4, f_sz = p->cfg.feats_f16 ? 2 : 4;
+  cer::g_launches = 0;
+  int rc;
+  // reference image + the owned source views, scaled by 1/8 (core/corr.py:30-31)
+  if ((rc = cer_nchw_to_nhwc(fmaps, fmaps_f16, p->feats, p->cfg.feats_f16, 1, 64, h, w, 0.125f, stream))) return rc;
+  const size_t img_in = (size_t)px * 64 * in_sz, img_f = (size_t)px * 64 * f_sz;
+  if ((rc = cer_nchw_to_nhwc((const char*)fmaps + (1 + view_begin) * img_in, fmaps_f16,
+                             (char*)p->feats + (1 + view_begin) * img_f, p->cfg.feats_f16, view_end - view_begin, 64,
+                             h, w, 0.125f, stream)))
+    return rc;
+  if ((rc = cer_nchw_to_nhwc(net, ctx_f16, p->net, 1, 1, 64, h, w, 1.f, stream))) return rc;
+  if ((rc = cer_nchw_to_nhwc(inp, ctx_f16, p->inp, 1, 1, 64, h, w, 1.f, stream))) return rc;
+  CER_CUDA(cudaMemsetAsync(p->disp, 0, px * 4, (cudaStream_t)stream));   // core/raft.py:52
+  if ((rc = cer_projection_matrices(poses, intrinsics, p->ii + view_begin, p->jj + view_begin,
+                                    view_end - view_begin, p->Pij + view_begin * 16, stream)))
+    return rc;
+  p->n_views = n_views;
+  p->vb = view_begin;
+  p->ve = view_end;
+  p->launches = cer::g_launches + 1;  // + memset
+  return CER_OK;
+}
+
+int cer_plan_build_stage(cer_plan* p, int s, cer_stream_t stream) {
+  CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_build_stage: bad stage");
+  const int D = p->cfg.D[s];
+  const double incre = (double)p->cfg.incre[s];
+  const float lo = (float)((D / 2) * incre);   // torch.tensor(nIncre // 2 * incre).float(), core/corr.py:60
+  cer::g_launches = 0;
+  int rc = cer_build_volume(p->feats, p->cfg.feats_f16, p->Pij + p->vb * 16, p->ii + p->vb, p->jj + p->vb,
+                            p->ve - p->vb, p->disp, s == 0, D, (float)incre, lo, p->origin, p->volume,
+                            1.f / (float)p->n_views, 0, p->cfg.h, p->cfg.w, stream);
+  p->launches += cer::g_launches;
+  return rc;
+}
+
+float* cer_plan_partial_volume(cer_plan* p, int s, size_t* n_floats) {
+  if (!p || s < 0 || s >= p->cfg.n_stages) return nullptr;
+  if (n_floats) *n_floats = (size_t)p->px * p->cfg.D[s];
+  return p->volume;
+}
+
+static int issue_iterations(cer_plan* p, int s, cudaStream_t stream) {
+  const int D = p->cfg.D[s];
+  const float incre = (float)p->cfg.incre[s];
+  for (int it = 0; it < p->cfg.iters[s]; ++it) {
+    int rc = cer_lookup(p->volume, 1, p->origin, p->disp, D, incre, 5, 3, p->corr, p->cfg.h, p->cfg.w, stream);
+    if (rc) return rc;
+    rc = update_step_hmma(p->blob, p->ws, p->net, p->inp, p->disp, p->corr, 1, nullptr, 1, s, p->cfg.h, p->cfg.w,
+                          stream);
+    if (rc) return rc;
+  }
+  return CER_OK;
+}
+
+int cer_plan_iterate_stage(cer_plan* p, int s, cer_stream_t stream_) {
+  CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_iterate_stage: bad stage");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (p->cfg.iters[s] == 0) return CER_OK;
+  if (!p->cfg.use_graph) {
+    cer::g_launches = 0;
+    int rc = issue_iterations(p, s, stream);
+    p->launches += cer::g_launches;
+    return rc;
+  }
+  if (!p->graph[s]) {
+    cudaGraph_t g = nullptr;
+    CER_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    cer::g_launches = 0;
+    int rc = issue_iterations(p, s, stream);
+    cudaError_t e = cudaStreamEndCapture(stream, &g);
+    if (rc || e != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      if (!rc) {
+        set_error("graph capture failed: %s", cudaGetErrorString(e));
+        rc = (int)e;
+      }
+      return rc;
+    }
+    p->graph_nodes[s] = cer::g_launches;
+    CER_CUDA(cudaGraphInstantiate(&p->graph[s], g, 0));
+    cudaGraphDestroy(g);
+  }
+  CER_CUDA(cudaGraphLaunch(p->graph[s], stream));
+  p->launches += p->graph_nodes[s];
+  return CER_OK;
+}
+
+int cer_plan_finish(cer_plan* p, float out_scale, float* disp_out, cer_stream_t stream) {
+  CER_REQUIRE(p && disp_out, "cer_plan_finish: null pointer");
+  CER_LAUNCH(scale_copy_kernel, ceil_div(p->px, 256), 256, 0, stream, p->disp, disp_out, out_scale, p->px);
+  p->launches += 1;
+  return check_launch("cer_plan_finish");
+}
+
+int cer_plan_run_device(cer_plan* p, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
+                        int ctx_f16, const float* poses, const float* intrinsics, int n_views, float out_scale,
+                        float* disp_out, cer_stream_t stream) {
+  int rc = cer_plan_prepare(p, fmaps, fmaps_f16, net, inp, ctx_f16, poses, intrinsics, n_views, 0, n_views, stream);
+  if (rc) return rc;
+  for (int s = 0; s < p->cfg.n_stages; ++s) {
+    if ((rc = cer_plan_build_stage(p, s, stream))) return rc;
+    if ((rc = cer_plan_iterate_stage(p, s, stream))) return rc;
+  }
+  return cer_plan_finish(p, out_scale, disp_out, stream);
+}
+
+int cer_plan_run_host(cer_plan* p, const void* fmaps, int fmaps_f16, const void* net, const void* inp, int ctx_f16,
+                      const float* poses, const float* intrinsics, int n_views, float out_scale, float* disp_out,
+                      cer_stream_t stream_) {
+  CER_REQUIRE(p && fmaps && net && inp && poses && intrinsics && disp_out, "cer_plan_run_host: null pointer");
+  CER_REQUIRE(n_views >= 1 && n_views <= p->cfg.max_views, "cer_plan_run_host: bad n_views");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long px = p->px;
+  const size_t fm_bytes = (size_t)(n_views + 1) * 64 * px * (fmaps_f16 ? 2 : 4);
+  const size_t ctx_bytes = (size_t)64 * px * (ctx_f16 ? 2 : 4);
+  const size_t need = align256(fm_bytes) + 2 * align256(ctx_bytes) + align256(px * 4);
+  if (need > p->stage_in_bytes) {
+    if (p->stage_in) cudaFree(p->stage_in);
+    p->stage_in = nullptr;
+    p->stage_in_bytes = 0;
+    CER_CUDA(cudaMalloc(&p->stage_in, need));
+    p->stage_in_bytes = need;
+  }
+  char* d_fm = (char*)p->stage_in;
+  char* d_net = d_fm + align256(fm_bytes);
+  char* d_inp = d_net + align256(ctx_bytes);
+  float* d_out = (float*)(d_inp + align256(ctx_bytes));
+  CER_CUDA(cudaMemcpyAsync(d_fm, fmaps, fm_bytes, cudaMemcpyHostToDevice, stream));
+  CER_CUDA(cudaMemcpyAsync(d_net, net, ctx_bytes, cudaMemcpyHostToDevice, stream));
+  CER_CUDA(cudaMemcpyAsync(d_inp, inp, ctx_bytes, cudaMemcpyHostToDevice, stream));
+  CER_CUDA(cudaMemcpyAsync(p->poses, poses, (n_views + 1) * 16 * 4, cudaMemcpyHostToDevice, stream));
+  CER_CUDA(cudaMemcpyAsync(p->intr, intrinsics, (n_views + 1) * 9 * 4, cudaMemcpyHostToDevice, stream));
+  int rc = cer_plan_run_device(p, d_fm, fmaps_f16, d_net, d_inp, ctx_f16, p->poses, p->intr, n_views, out_scale,
+                               d_out, stream);
+  if (rc) return rc;
+  CER_CUDA(cudaMemcpyAsync(disp_out, d_out, px * 4, cudaMemcpyDeviceToHost, stream));
+  CER_CUDA(cudaStreamSynchronize(stream));
+  return CER_OK;
+}
+
+long long cer_plan_last_launch_count(const cer_plan* p) { return p ? p->launches : 0; }
+
+}  // extern "C"

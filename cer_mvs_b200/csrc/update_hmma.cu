@@ -1,0 +1,575 @@
+// UpdateBlock.forward (core/update.py:87-120), v1: implicit-GEMM 3x3 convolutions on mma.sync
+// (m16n8k16, fp16 operands, fp32 accumulate) with the element-wise GRU algebra fused into the
+// epilogues.  NHWC fp16 activations, 64 channels per tensor, one CTA = 8 x 16 pixels.
+//
+// Kernels per iteration:
+//   K0 disp_encode     dn = fp16(100 * (unfold7x7(disp) - disp))                      update.py:80-85,97
+//   K1 corr_enc1       e1 = relu(conv1x1(mean_v corr))                                update.py:103,62-63
+//   K2 conv3x3<64>     e  = relu(conv3x3(e1))                                         update.py:64-65
+//   K3 conv3x3<192>    z = sigma(.), r*net, qx = convq over [inp|dn|e] + bq           update.py:20-23
+//   K4 conv3x3<64>     q = tanh(convq(r*net) + qx); net = (1-z) net + z q             update.py:23-24
+//   K5 conv3x3<256>    d = relu(conv3x3(net)); s9[p][t] = w2[t] . d[p]                update.py:69-70
+//   K6 disp_update     delta = 0.01 * (b + sum_t s9[p+off_t][t]); disp += delta       update.py:71,114 raft.py:101
+#include <string.h>
+
+#include "common.cuh"
+#include "update_blob.h"
+
+namespace cer {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float h_round(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------
+// K0: disparity-neighbourhood encoder -> [px][64] fp16 (channels 49..63 zero)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) disp_encode_kernel(const float* __restrict__ disp, __half* __restrict__ dn,
+                                                         int h, int w) {
+  const long long px = (long long)h * w;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel*8 + group of 8 channels
+  if (idx >= px * 8) return;
+  const long long p = idx >> 3;
+  const int g = (int)(idx & 7);
+  const int x = (int)(p % w), y = (int)(p / w);
+  const float c = __ldg(disp + p);
+  __align__(16) __half v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = g * 8 + e;
+    float val = 0.f;
+    if (k < kDispEnc) {
+      const int yy = y + k / 7 - 3, xx = x + k % 7 - 3;
+      const float nb = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(disp + (long long)yy * w + xx) : 0.f;
+      val = __fmul_rn(100.f, __fsub_rn(nb, c));
+    }
+    v[e] = __float2half_rn(val);
+  }
+  *reinterpret_cast<uint4*>(dn + p * 64 + g * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: e1 = relu(conv1x1(mean over slots of corr [slots][33][px])) -> [px][64] fp16
+// ------------------------------------------------------------------------------------------
+constexpr int kA1Pitch = kCorrK + 8;   // halfs
+constexpr int kW1Pitch = kHid + 8;
+
+__global__ void __launch_bounds__(256) corr_enc1_kernel(const float* __restrict__ corr, int slots,
+                                                       const __half* __restrict__ w1, const float* __restrict__ b1,
+                                                       __half* __restrict__ e1, long long px) {
+  __shared__ __align__(16) __half sA[128 * kA1Pitch];
+  __shared__ __align__(16) __half sW[kCorrK * kW1Pitch];
+  const long long p0 = (long long)blockIdx.x * 128;
+  const int tid = threadIdx.x;
+  const float inv = 1.f / (float)slots;
+  for (int i = tid; i < kCorrK * 128; i += 256) {
+    const int k = i >> 7, pl = i & 127;
+    float v = 0.f;
+    if (k < kCorrPlanes && p0 + pl < px) {
+      for (int s = 0; s < slots; ++s) v += __ldg(corr + ((long long)s * kCorrPlanes + k) * px + p0 + pl);
+      v *= inv;
+    }
+    sA[pl * kA1Pitch + k] = __float2half_rn(v);
+  }
+  for (int i = tid; i < kCorrK * kHid / 8; i += 256) {
+    const int k = i / (kHid / 8), c = i % (kHid / 8);
+    *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const uint32_t aBase = smem_u32(sA) + ((warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kA1Pitch + 8 * (lane >> 4)) * 2;
+  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * kW1Pitch + 8 * (lane >> 4)) * 2;
+#pragma unroll
+  for (int k16 = 0; k16 < kCorrK / 16; ++k16) {
+    uint32_t a[4];
+    ldmatrix_x4(a, aBase + k16 * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, bBase + (k16 * 16 * kW1Pitch + j * 16) * 2);
+      mma16816(acc[2 * j], a, b[0], b[1]);
+      mma16816(acc[2 * j + 1], a, b[2], b[3]);
+    }
+  }
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const long long p = p0 + warp * 16 + g + 8 * half;
+    if (p >= px) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = j * 8 + q * 2;
+      const float v0 = fmaxf(h_round(acc[j][2 * half] + __ldg(b1 + n)), 0.f);
+      const float v1 = fmaxf(h_round(acc[j][2 * half + 1] + __ldg(b1 + n + 1)), 0.f);
+      *reinterpret_cast<__half2*>(e1 + p * 64 + n) = __floats2half2_rn(v0, v1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 implicit-GEMM convolution
+// ------------------------------------------------------------------------------------------
+constexpr int TH = 8, TW = 16;                 // output tile (128 pixels)
+constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
+constexpr int HALO_PX = HALO_W * HALO_H;       // 180
+constexpr int A_PITCH = 64 + 8;                // halfs per halo pixel (144 B, conflict-free ldmatrix)
+constexpr int A_BYTES = HALO_PX * A_PITCH * 2; // 25920
+constexpr int NSTAGE = 3;
+
+enum Epilogue { EPI_RELU = 0, EPI_GATES = 1, EPI_GRUOUT = 2, EPI_DELTA = 3 };
+
+struct ConvArgs {
+  const __half* src[4];
+  int n_src;
+  const __half* wpk;   // [n_src][9][64][N_TILE]
+  const float* bias;   // [N_TILE] or null
+  int h, w;
+  __half* out_h;       // EPI_RELU: [px][64]
+  __half* net;         // EPI_GATES: read; EPI_GRUOUT: read + written in place
+  __half* z;           // EPI_GATES: write; EPI_GRUOUT: read
+  __half* rnet;        // EPI_GATES: write
+  float* qx;           // EPI_GATES: write; EPI_GRUOUT: read
+  const float* w2;     // EPI_DELTA: [9][256]
+  float* s9;           // EPI_DELTA: [px][9]
+};
+
+template <int N_TILE>
+struct ConvSmem {
+  static constexpr int B_PITCH = N_TILE + 8;             // halfs
+  static constexpr int B_BYTES = 64 * B_PITCH * 2;
+  static constexpr int TOTAL = 2 * A_BYTES + NSTAGE * B_BYTES + (N_TILE == 256 ? (9 * 256 + 128 * 9) * 4 : 0);
+};
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) {
+  using S = ConvSmem<N_TILE>;
+  constexpr int NW = N_TILE / 4;     // columns per warp
+  constexpr int NJ = NW / 8;         // n8 tiles per warp
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + 2 * A_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int tiles_x = (a.w + TW - 1) / TW;
+  const int x0 = (blockIdx.x % tiles_x) * TW, y0 = (blockIdx.x / tiles_x) * TH;
+  const int n_steps = a.n_src * 9;
+
+  auto load_A = [&](int chunk) {
+    const __half* src = a.src[chunk];
+    const uint32_t dst0 = sA + (chunk & 1) * A_BYTES;
+    for (int i = tid; i < HALO_PX * 8; i += 256) {
+      const int hp = i >> 3, c = i & 7;
+      const int yy = y0 - 1 + hp / HALO_W, xx = x0 - 1 + hp % HALO_W;
+      const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
+      const __half* g = src + ((long long)(ok ? yy : 0) * a.w + (ok ? xx : 0)) * 64 + c * 8;
+      cp_async16(dst0 + hp * (A_PITCH * 2) + c * 16, g, ok);
+    }
+  };
+  auto load_B = [&](int step) {
+    const __half* src = a.wpk + (long long)step * 64 * N_TILE;
+    const uint32_t dst0 = sB + (step % NSTAGE) * S::B_BYTES;
+    constexpr int CPR = N_TILE / 8;  // 16-byte chunks per row
+    for (int i = tid; i < 64 * CPR; i += 256) {
+      const int k = i / CPR, c = i % CPR;
+      cp_async16(dst0 + k * (S::B_PITCH * 2) + c * 16, src + k * N_TILE + c * 8, true);
+    }
+  };
+
+  float acc[4][NJ][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  // prologue: steps 0 and 1
+  load_A(0);
+  load_B(0);
+  cp_async_commit();
+  if (n_steps > 1) load_B(1);
+  cp_async_commit();
+
+  const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);   // ldmatrix row supplied by this lane
+  const int lcol = 8 * (lane >> 4);                      // ldmatrix column offset (halfs)
+
+  for (int step = 0; step < n_steps; ++step) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    {  // prefetch step + 2 (its B buffer was consumed in step - 1)
+      const int nxt = step + NSTAGE - 1;
+      if (nxt < n_steps) {
+        if (nxt % 9 == 0) load_A(nxt / 9);
+        load_B(nxt);
+      }
+      cp_async_commit();
+    }
+    const int chunk = step / 9, tap = step % 9;
+    const int ky = tap / 3, kx = tap % 3;
+    const uint32_t aBuf = sA + (chunk & 1) * A_BYTES;
+    const uint32_t bBuf = sB + (step % NSTAGE) * S::B_BYTES;
+#pragma unroll
+    for (int k16 = 0; k16 < 4; ++k16) {
+      uint32_t af[4][4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int hp = (wm * 4 + mi + ky) * HALO_W + kx + lrow;
+        ldmatrix_x4(af[mi], aBuf + hp * (A_PITCH * 2) + (k16 * 16 + lcol) * 2);
+      }
+#pragma unroll
+      for (int jp = 0; jp < NJ / 2; ++jp) {
+        uint32_t bf[4];
+        ldmatrix_x4_trans(bf, bBuf + (k16 * 16 + lrow) * (S::B_PITCH * 2) + (wn * NW + jp * 16 + lcol) * 2);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          mma16816(acc[mi][2 * jp], af[mi], bf[0], bf[1]);
+          mma16816(acc[mi][2 * jp + 1], af[mi], bf[2], bf[3]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---------------- epilogues ----------------
+  const int g = lane >> 2, q = lane & 3;
+  if (EPI == EPI_DELTA) {
+    // d = relu(fp16(acc + b)); s9[p][t] = sum_n w2[t][n] * d[n]  (second delta conv as 9 per-pixel dots)
+    float* sW2 = reinterpret_cast<float*>(smem + 2 * A_BYTES + NSTAGE * S::B_BYTES);
+    float* sS9 = sW2 + 9 * 256;
+    __syncthreads();
+    for (int i = tid; i < 9 * 256; i += 256) sW2[i] = __ldg(a.w2 + i);
+    for (int i = tid; i < 128 * 9; i += 256) sS9[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      float t0[9], t1[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) t0[t] = t1[t] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int n = wn * NW + j * 8 + q * 2;
+        const float bn0 = __ldg(a.bias + n), bn1 = __ldg(a.bias + n + 1);
+        const float d00 = fmaxf(h_round(acc[mi][j][0] + bn0), 0.f), d01 = fmaxf(h_round(acc[mi][j][1] + bn1), 0.f);
+        const float d10 = fmaxf(h_round(acc[mi][j][2] + bn0), 0.f), d11 = fmaxf(h_round(acc[mi][j][3] + bn1), 0.f);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float2 wv = *reinterpret_cast<const float2*>(sW2 + t * 256 + n);
+          t0[t] = fmaf(d00, wv.x, fmaf(d01, wv.y, t0[t]));
+          t1[t] = fmaf(d10, wv.x, fmaf(d11, wv.y, t1[t]));
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        t0[t] += __shfl_xor_sync(0xffffffffu, t0[t], 1);
+        t0[t] += __shfl_xor_sync(0xffffffffu, t0[t], 2);
+        t1[t] += __shfl_xor_sync(0xffffffffu, t1[t], 1);
+        t1[t] += __shfl_xor_sync(0xffffffffu, t1[t], 2);
+      }
+      if (q == 0) {
+        const int pl = (wm * 4 + mi) * TW + g;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          atomicAdd(sS9 + pl * 9 + t, t0[t]);
+          atomicAdd(sS9 + (pl + 8) * 9 + t, t1[t]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 128 * 9; i += 256) {
+      const int pl = i / 9, t = i % 9;
+      const int yy = y0 + pl / TW, xx = x0 + pl % TW;
+      if (yy < a.h && xx < a.w) a.s9[((long long)yy * a.w + xx) * 9 + t] = sS9[i];
+    }
+    return;
+  }
+
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int yy = y0 + wm * 4 + mi;
+    if (yy >= a.h) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int xx = x0 + g + 8 * half;
+      if (xx >= a.w) continue;
+      const long long p = (long long)yy * a.w + xx;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int n = wn * NW + j * 8 + q * 2;
+        float v0 = acc[mi][j][2 * half], v1 = acc[mi][j][2 * half + 1];
+        if (EPI == EPI_RELU) {
+          v0 = fmaxf(h_round(v0 + __ldg(a.bias + n)), 0.f);
+          v1 = fmaxf(h_round(v1 + __ldg(a.bias + n + 1)), 0.f);
+          *reinterpret_cast<__half2*>(a.out_h + p * 64 + n) = __floats2half2_rn(v0, v1);
+        } else if (EPI == EPI_GATES) {
+          v0 += __ldg(a.bias + n);
+          v1 += __ldg(a.bias + n + 1);
+          if (n < 64) {            // z = sigmoid(convz)                                update.py:20-21
+            const float z0 = sigmoid_f(h_round(v0)), z1 = sigmoid_f(h_round(v1));
+            *reinterpret_cast<__half2*>(a.z + p * 64 + n) = __floats2half2_rn(z0, z1);
+          } else if (n < 128) {    // r = sigmoid(convr); r * net                         update.py:22-23
+            const float r0 = h_round(sigmoid_f(h_round(v0))), r1 = h_round(sigmoid_f(h_round(v1)));
+            const float2 nt = __half22float2(*reinterpret_cast<const __half2*>(a.net + p * 64 + (n - 64)));
+            *reinterpret_cast<__half2*>(a.rnet + p * 64 + (n - 64)) = __floats2half2_rn(r0 * nt.x, r1 * nt.y);
+          } else {                 // x-part of convq, kept in fp32 until K4 adds the r*net part
+            *reinterpret_cast<float2*>(a.qx + p * 64 + (n - 128)) = make_float2(v0, v1);
+          }
+        } else if (EPI == EPI_GRUOUT) {  // q = tanh(convq); net = (1-z)*net + z*q          update.py:23-24
+          const float2 qx = *reinterpret_cast<const float2*>(a.qx + p * 64 + n);
+          const float2 zz = __half22float2(*reinterpret_cast<const __half2*>(a.z + p * 64 + n));
+          const float2 nt = __half22float2(*reinterpret_cast<const __half2*>(a.net + p * 64 + n));
+          const float q0 = h_round(tanhf(h_round(v0 + qx.x))), q1 = h_round(tanhf(h_round(v1 + qx.y)));
+          const float n0 = h_round(h_round(h_round(1.f - zz.x) * nt.x) + h_round(zz.x * q0));
+          const float n1 = h_round(h_round(h_round(1.f - zz.y) * nt.y) + h_round(zz.y * q1));
+          *reinterpret_cast<__half2*>(a.net + p * 64 + n) = __floats2half2_rn(n0, n1);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t])); disp += delta
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) disp_update_kernel(const float* __restrict__ s9, const float* __restrict__ bd1,
+                                                         float* __restrict__ disp, float* __restrict__ delta,
+                                                         int apply, int h, int w) {
+  const long long px = (long long)h * w;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= px) return;
+  const int x = (int)(p % w), y = (int)(p / w);
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += __ldg(s9 + ((long long)yy * w + xx) * 9 + t);
+  }
+  const float d = h_round(0.01f * h_round(s + __ldg(bd1)));
+  if (delta) delta[p] = d;
+  if (apply) disp[p] += d;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct UpdateWs {
+  __half *dn, *e1, *e, *z, *rnet;
+  float *qx, *s9;
+  size_t total;
+};
+
+static UpdateWs carve_ws(void* base, long long px) {
+  UpdateWs w{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return (char*)base + r; };
+  w.dn = (__half*)take(px * 64 * 2);
+  w.e1 = (__half*)take(px * 64 * 2);
+  w.e = (__half*)take(px * 64 * 2);
+  w.z = (__half*)take(px * 64 * 2);
+  w.rnet = (__half*)take(px * 64 * 2);
+  w.qx = (float*)take(px * 64 * 4);
+  w.s9 = (float*)take(px * 9 * 4);
+  w.total = o;
+  return w;
+}
+
+template <int N_TILE, int EPI>
+static int configure_conv() {
+  CER_CUDA(cudaFuncSetAttribute(conv3x3_hmma_kernel<N_TILE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvSmem<N_TILE>::TOTAL));
+  return CER_OK;
+}
+
+// Opt in to >48 KB dynamic shared memory once per process (not capturable, so done up front).
+int update_configure() {
+  static bool done = false;
+  if (done) return CER_OK;
+  int rc;
+  if ((rc = configure_conv<64, EPI_RELU>())) return rc;
+  if ((rc = configure_conv<192, EPI_GATES>())) return rc;
+  if ((rc = configure_conv<64, EPI_GRUOUT>())) return rc;
+  if ((rc = configure_conv<256, EPI_DELTA>())) return rc;
+  done = true;
+  return CER_OK;
+}
+
+template <int N_TILE, int EPI>
+static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
+  constexpr int smem = ConvSmem<N_TILE>::TOTAL;
+  const int tiles = ((a.w + TW - 1) / TW) * ((a.h + TH - 1) / TH);
+  CER_LAUNCH((conv3x3_hmma_kernel<N_TILE, EPI>), tiles, 256, smem, stream, a);
+  return check_launch("conv3x3_hmma");
+}
+
+int update_step_hmma(const void* blob, void* workspace, void* net, const void* inp, float* disp, const float* corr,
+                     int slots, float* delta, int apply_delta, int stage, int h, int w, cudaStream_t stream) {
+  const BlobLayout L = blob_layout();
+  const char* B = (const char*)blob;
+  const long long px = (long long)h * w;
+  UpdateWs ws = carve_ws(workspace, px);
+  int rc;
+  if ((rc = update_configure())) return rc;
+  CER_LAUNCH(disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
+  CER_LAUNCH(corr_enc1_kernel, ceil_div(px, 128), 256, 0, stream, corr, slots, (const __half*)(B + L.w1),
+             (const float*)(B + L.b1), ws.e1, px);
+  if ((rc = check_launch("update prologue"))) return rc;
+  ConvArgs a{};
+  a.h = h;
+  a.w = w;
+  // K2
+  a.src[0] = ws.e1; a.n_src = 1; a.wpk = (const __half*)(B + L.w2); a.bias = (const float*)(B + L.b2); a.out_h = ws.e;
+  if ((rc = launch_conv<64, EPI_RELU>(a, stream))) return rc;
+  // K3
+  a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = ws.dn; a.src[3] = ws.e; a.n_src = 4;
+  a.wpk = (const __half*)(B + L.wg); a.bias = (const float*)(B + L.bg);
+  a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
+  if ((rc = launch_conv<192, EPI_GATES>(a, stream))) return rc;
+  // K4
+  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.bias = nullptr;
+  if ((rc = launch_conv<64, EPI_GRUOUT>(a, stream))) return rc;
+  // K5
+  a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]);
+  a.bias = (const float*)(B + L.bd0[stage]); a.w2 = (const float*)(B + L.wd1[stage]); a.s9 = ws.s9;
+  if ((rc = launch_conv<256, EPI_DELTA>(a, stream))) return rc;
+  // K6
+  CER_LAUNCH(disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, (const float*)(B + L.bd1[stage]), disp,
+             delta, apply_delta, h, w);
+  return check_launch("disp_update");
+}
+
+}  // namespace cer
+
+using namespace cer;
+
+extern "C" {
+
+size_t cer_update_blob_bytes(void) { return blob_layout().total; }
+
+size_t cer_update_workspace_bytes(int h, int w) { return carve_ws(nullptr, (long long)h * w).total; }
+
+int cer_pack_update_weights(const float* const* w, void* blob_host) {
+  CER_REQUIRE(w && blob_host, "cer_pack_update_weights: null pointer");
+  for (int i = 0; i < 18; ++i) CER_REQUIRE(w[i], "cer_pack_update_weights: tensor %d is null", i);
+  const BlobLayout L = blob_layout();
+  char* B = (char*)blob_host;
+  memset(B, 0, L.total);
+  auto H = [](float v) { return __float2half_rn(v); };
+  // corr_encoder.0: [64][33][1][1] -> w1[k][n]
+  {
+    __half* d = (__half*)(B + L.w1);
+    for (int n = 0; n < 64; ++n)
+      for (int k = 0; k < kCorrPlanes; ++k) d[k * 64 + n] = H(w[0][n * kCorrPlanes + k]);
+    memcpy(B + L.b1, w[1], 64 * 4);
+  }
+  // generic 3x3 OIHW [cout][cin][3][3] slice -> [tap][k][n_total] at column offset n0
+  auto pack3x3 = [&](const float* src, int cout, int cin_total, int cin0, int cin_n, __half* dst, int n_total, int n0) {
+    for (int o = 0; o < cout; ++o)
+      for (int k = 0; k < cin_n; ++k)
+        for (int t = 0; t < 9; ++t)
+          dst[((long long)t * 64 + k) * n_total + n0 + o] = H(src[((long long)o * cin_total + cin0 + k) * 9 + t]);
+  };
+  pack3x3(w[2], 64, 64, 0, 64, (__half*)(B + L.w2), 64, 0);
+  memcpy(B + L.b2, w[3], 64 * 4);
+  // gates: chunk order net | inp | dn | e = input channels 0 | 64 | 128 (49) | 177
+  const int cin0[4] = {0, 64, 128, 177};
+  const int cinn[4] = {64, 64, kDispEnc, 64};
+  for (int c = 0; c < 4; ++c) {
+    __half* dst = (__half*)(B + L.wg) + (long long)c * 9 * 64 * kGateN;
+    pack3x3(w[4], 64, kGruIn, cin0[c], cinn[c], dst, kGateN, 0);     // convz
+    pack3x3(w[6], 64, kGruIn, cin0[c], cinn[c], dst, kGateN, 64);    // convr
+    if (c > 0) pack3x3(w[8], 64, kGruIn, cin0[c], cinn[c], dst, kGateN, 128);  // convq, x part
+  }
+  {
+    float* bg = (float*)(B + L.bg);
+    memcpy(bg, w[5], 64 * 4);
+    memcpy(bg + 64, w[7], 64 * 4);
+    memcpy(bg + 128, w[9], 64 * 4);
+  }
+  pack3x3(w[8], 64, kGruIn, 0, 64, (__half*)(B + L.wq), 64, 0);      // convq, r*net part
+  for (int s = 0; s < 2; ++s) {
+    const float* w0 = w[10 + 4 * s];
+    const float* b0 = w[11 + 4 * s];
+    const float* w1 = w[12 + 4 * s];
+    const float* b1 = w[13 + 4 * s];
+    pack3x3(w0, 256, 64, 0, 64, (__half*)(B + L.wd0[s]), 256, 0);
+    memcpy(B + L.bd0[s], b0, 256 * 4);
+    float* d = (float*)(B + L.wd1[s]);
+    for (int c = 0; c < 256; ++c)
+      for (int t = 0; t < 9; ++t) d[t * 256 + c] = __half2float(H(w1[c * 9 + t]));
+    *(float*)(B + L.bd1[s]) = b1[0];
+  }
+  // biases are rounded to fp16 by autocast as well (conv2d casts every floating argument)
+  auto round_bias = [&](size_t off, int n) {
+    float* b = (float*)(B + off);
+    for (int i = 0; i < n; ++i) b[i] = __half2float(H(b[i]));
+  };
+  round_bias(L.b1, 64);
+  round_bias(L.b2, 64);
+  round_bias(L.bg, 192);
+  for (int s = 0; s < 2; ++s) {
+    round_bias(L.bd0[s], 256);
+    round_bias(L.bd1[s], 1);
+  }
+  return CER_OK;
+}
+
+int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e, int h,
+                 int w, cer_stream_t stream) {
+  CER_REQUIRE(blob && workspace && net && inp && dn && e && h > 0 && w > 0, "cer_gru_step: bad arguments");
+  int rc;
+  if ((rc = update_configure())) return rc;
+  const BlobLayout L = blob_layout();
+  const char* B = (const char*)blob;
+  UpdateWs ws = carve_ws(workspace, (long long)h * w);
+  ConvArgs a{};
+  a.h = h; a.w = w;
+  a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = (const __half*)dn; a.src[3] = (const __half*)e;
+  a.n_src = 4; a.wpk = (const __half*)(B + L.wg); a.bias = (const float*)(B + L.bg);
+  a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
+  if ((rc = launch_conv<192, EPI_GATES>(a, (cudaStream_t)stream))) return rc;
+  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.bias = nullptr;
+  return launch_conv<64, EPI_GRUOUT>(a, (cudaStream_t)stream);
+}
+
+int cer_update_step(const void* blob, void* workspace, void* net, const void* inp, float* disp, const float* corr,
+                    int slots, float* delta, int apply_delta, int stage, int h, int w, cer_stream_t stream) {
+  CER_REQUIRE(blob && workspace && net && inp && disp && corr, "cer_update_step: null pointer");
+  CER_REQUIRE(slots > 0 && h > 0 && w > 0 && (stage == 0 || stage == 1), "cer_update_step: bad arguments");
+  CER_REQUIRE(aligned16(blob) && aligned16(workspace) && aligned16(net) && aligned16(inp),
+              "cer_update_step: pointers must be 16-byte aligned");
+  return update_step_hmma(blob, workspace, net, inp, disp, corr, slots, delta, apply_delta, stage, h, w,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""``DepthHotPath``: the stage / iteration loop of ``RAFT.forward`` (core/raft.py:75-108) behind one
+native plan (``cer_plan`` in csrc/plan.cu): feature layout, projection matrices, fused cost-volume
+build, and per stage a CUDA-graph replay of {lookup, UpdateBlock} x iterations, everything resident
+on the device in the kernels' layouts.
+
+    hp = DepthHotPath(h1, w1, max_views=10, cascade=[(64, 64, 8), (-1, 320, 8)])
+    hp.load_update_block(state_dict)                   # reference UpdateBlock keys (core/update.py)
+    disp = hp(fmaps, net, inp, poses, intrinsics, scale)      # device tensors -> [1,1,h1,w1]
+    disp = hp.run_host(fmaps_np, net_np, inp_np, poses_np, intrinsics_np, scale)   # host buffers
+
+Multi-GPU: ``forward_view_sharded`` lets every rank build the partial volume
+of its own source views, sums the partials with one all-reduce per stage, then iterates replicated.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .update import pack_update_weights
+
+
+def stage_params(cascade, num_levels=3, radius=5):
+    """core/raft.py:76-81 -> [(D, incre, iters)]."""
+    out = []
+    for nIncre, incre, nIters in cascade:
+        if nIncre == -1:
+            nIncre = (2 * radius + 1) * 2 ** (num_levels - 1)
+        out.append((int(nIncre), 0.0025 / incre, int(nIters)))
+    return out
+
+
+class _DevView:
+    """Expose plan-owned device memory to torch (zero-copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class DepthHotPath:
+    def __init__(self, h1, w1, max_views, cascade=((64, 64, 8), (-1, 320, 8)), feats_f16=True, use_graph=True,
+                 device=None):
+        self.h1, self.w1, self.max_views = int(h1), int(w1), int(max_views)
+        self.stages = stage_params(cascade)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        cfg = _lib.PlanConfig()
+        cfg.h, cfg.w, cfg.max_views, cfg.n_stages = self.h1, self.w1, self.max_views, len(self.stages)
+        for s, (D, incre, iters) in enumerate(self.stages):
+            cfg.D[s], cfg.incre[s], cfg.iters[s] = D, incre, iters
+        cfg.feats_f16, cfg.use_graph = int(feats_f16), int(use_graph)
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cer_plan_create(C.byref(cfg), C.byref(self._plan)), "cer_plan_create")
+        self._out = torch.empty(1, 1, self.h1, self.w1, device=self.device, dtype=torch.float32)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                _lib.lib().cer_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    # ---- weights ----
+    def load_update_block(self, sd):
+        """sd: UpdateBlock state dict (reference keys; tensors or arrays; a 'module.update_block.' or
+        'update_block.' prefix from a RAFT / DataParallel checkpoint is stripped, inference.py:31-35)."""
+        clean = {}
+        for k, v in sd.items():
+            for pre in ("module.", "update_block."):
+                if k.startswith(pre):
+                    k = k[len(pre):]
+            clean[k] = v
+        blob = pack_update_weights(clean)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cer_plan_set_weights(self._plan, blob.ctypes.data), "cer_plan_set_weights")
+
+    # ---- input prep shared by the device paths (core/raft.py:35-39) ----
+    def _prep_cameras(self, poses, intrinsics, scale):
+        P = poses.reshape(-1, 4, 4).to(self.device, torch.float32).clone()
+        if scale is not None:
+            P[:, :3, 3] *= float(scale)
+        K = intrinsics.reshape(-1, 3, 3).to(self.device, torch.float32).clone()
+        K[:, :2] /= 4
+        return P.contiguous(), K.contiguous()
+
+    def _check_maps(self, fmaps, net, inp):
+        if fmaps.dim() != 5 or fmaps.shape[0] != 1 or fmaps.shape[2] != 64 or tuple(fmaps.shape[3:]) != (self.h1, self.w1):
+            raise RuntimeError(f"fmaps must be [1,V+1,64,{self.h1},{self.w1}]")
+        n_views = fmaps.shape[1] - 1
+        if not 1 <= n_views <= self.max_views:
+            raise RuntimeError(f"number of source views {n_views} outside 1..{self.max_views}")
+        for t in (fmaps, net, inp):
+            if not t.is_cuda:
+                raise RuntimeError("DepthHotPath: device tensors expected (use run_host for host buffers)")
+            if t.dtype not in (torch.float16, torch.float32):
+                raise RuntimeError("DepthHotPath: float16 or float32 maps expected")
+        if net.dtype != inp.dtype:
+            raise RuntimeError("net and inp must share a dtype")
+        return n_views
+
+    def __call__(self, fmaps, net, inp, poses, intrinsics, scale=1.0, out=None):
+        n_views = self._check_maps(fmaps, net, inp)
+        with torch.cuda.device(self.device):
+            P, K = self._prep_cameras(poses, intrinsics, scale)
+            fmaps, net, inp = fmaps.contiguous(), net.contiguous(), inp.contiguous()
+            out = self._out if out is None else out
+            _lib.check(_lib.lib().cer_plan_run_device(
+                self._plan, fmaps.data_ptr(), int(fmaps.dtype == torch.float16), net.data_ptr(), inp.data_ptr(),
+                int(net.dtype == torch.float16), P.data_ptr(), K.data_ptr(), n_views,
+                1.0 if scale is None else float(scale), out.data_ptr(), _lib.stream_ptr()), "cer_plan_run_device")
+        return out
+
+    def run_host(self, fmaps, net, inp, poses, intrinsics, scale=1.0, out=None):
+        """Host buffers in (numpy arrays or CPU tensors, ideally pinned), host disparity out.
+        poses / intrinsics as RAFT.forward receives them (scaling and the /4 are done here)."""
+        def as_np(x):
+            return x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        fm, nt, ip = as_np(fmaps), as_np(net), as_np(inp)
+        n_views = fm.shape[1] - 1
+        P = np.array(as_np(poses), dtype=np.float32).reshape(-1, 4, 4)
+        if scale is not None:
+            P[:, :3, 3] *= np.float32(scale)
+        K = np.array(as_np(intrinsics), dtype=np.float32).reshape(-1, 3, 3)
+        K[:, :2] /= 4
+        if out is None:
+            out = np.empty((1, 1, self.h1, self.w1), np.float32)
+        o = as_np(out)
+        for a in (fm, nt, ip):
+            if a.dtype not in (np.float16, np.float32) or not a.flags["C_CONTIGUOUS"]:
+                raise RuntimeError("run_host: contiguous float16/float32 arrays expected")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cer_plan_run_host(
+                self._plan, fm.ctypes.data, int(fm.dtype == np.float16), nt.ctypes.data, ip.ctypes.data,
+                int(nt.dtype == np.float16), P.ctypes.data, K.ctypes.data, n_views,
+                1.0 if scale is None else float(scale), o.ctypes.data, _lib.stream_ptr()), "cer_plan_run_host")
+        return out
+
+    def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None):
+        """One depth map over all ranks of ``group``: rank g builds views [g*V/G, (g+1)*V/G), one
+        all-reduce(sum) of the partial mean volume per stage, replicated GRU loop."""
+        import torch.distributed as dist
+        from .dist import view_range
+        n_views = self._check_maps(fmaps, net, inp)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        vb, ve = view_range(n_views, rank, world)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr()
+            P, K = self._prep_cameras(poses, intrinsics, scale)
+            fmaps, net, inp = fmaps.contiguous(), net.contiguous(), inp.contiguous()
+            out = self._out if out is None else out
+            if ve > vb:
+                _lib.check(L.cer_plan_prepare(self._plan, fmaps.data_ptr(), int(fmaps.dtype == torch.float16),
+                                              net.data_ptr(), inp.data_ptr(), int(net.dtype == torch.float16),
+                                              P.data_ptr(), K.data_ptr(), n_views, vb, ve, st), "cer_plan_prepare")
+            else:
+                raise RuntimeError("more ranks than source views: use replica mode for the surplus ranks")
+            for s in range(len(self.stages)):
+                _lib.check(L.cer_plan_build_stage(self._plan, s, st), "cer_plan_build_stage")
+                n = C.c_size_t()
+                ptr = L.cer_plan_partial_volume(self._plan, s, C.byref(n))
+                vol = torch.as_tensor(_DevView(ptr, n.value), device=self.device)
+                dist.all_reduce(vol, op=dist.ReduceOp.SUM, group=group)
+                _lib.check(L.cer_plan_iterate_stage(self._plan, s, st), "cer_plan_iterate_stage")
+            _lib.check(L.cer_plan_finish(self._plan, 1.0 if scale is None else float(scale), out.data_ptr(), st),
+                       "cer_plan_finish")
+        return out
+
+    @property
+    def last_launch_count(self):
+        return int(_lib.lib().cer_plan_last_launch_count(self._plan))
+
+    @property
+    def workspace_bytes(self):
+        return int(_lib.lib().cer_plan_workspace_bytes(self._plan))

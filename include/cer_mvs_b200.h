@@ -1,0 +1,179 @@
+/* cer_mvs_b200 -- C ABI of the B200-native CER-MVS inference hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch types) and a CUDA
+ * stream handle, never allocates device memory behind the caller's back (except the opaque
+ * `cer_plan`, which owns its workspace), never synchronises unless it says so, and returns 0 on
+ * success or a non-zero cudaError_t-style code (`cer_last_error()` gives the text).
+ * All device pointers must be 16-byte aligned.  Launches go on the given stream and are CUDA-graph
+ * capturable.
+ *
+ * Each function cites the interface of the reference (princeton-vl/CER-MVS @ 8062ddf) it replaces.
+ */
+#ifndef CER_MVS_B200_H
+#define CER_MVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cer_stream_t; /* cudaStream_t */
+
+#define CER_OK 0
+#define CER_ERR_INVALID 1001   /* bad argument (shape / alignment / unsupported size) */
+#define CER_ERR_NO_DEVICE 1002 /* no sm_100 device: the library has no CPU fallback */
+
+int cer_abi_version(void);
+const char* cer_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x). */
+int cer_device_check(void);
+
+/* ---- alt_cuda_corr.forward ---------------------------------------------------------------
+ * Replaces corr_forward / corr_cuda_forward / corr_forward_kernel
+ * (alt_cuda_corr/correlation.cpp:23-33,52; correlation_kernel.cu:18-119,260-286).
+ * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,N,H1,W1,2] (x,y in fmap2 pixels), all fp32
+ * contiguous; corr [B,N,(2r+1)^2,H1,W1] fp32 is fully overwritten (the reference zero-fills and
+ * accumulates).  Any radius >= 0, any C >= 1. */
+int cer_corr_forward_f32(const float* fmap1, const float* fmap2, const float* coords, float* corr,
+                         int B, int H1, int W1, int H2, int W2, int C, int N, int radius,
+                         cer_stream_t stream);
+
+/* ---- feature / context layout ------------------------------------------------------------
+ * Replaces the permute / "/8.0" / contiguous / float chain of direct_corr (core/corr.py:29-35).
+ * src [n,C,h,w] (fp16 or fp32) -> dst [n,h,w,C] (fp16 or fp32), multiplied by `scale`. */
+int cer_nchw_to_nhwc(const void* src, int src_f16, void* dst, int dst_f16, int n, int C, int h, int w,
+                     float scale, cer_stream_t stream);
+/* Same with a destination channel pitch dstC >= C (channels C..dstC-1 are written as zero). */
+int cer_nchw_to_nhwc_pad(const void* src, int src_f16, void* dst, int dst_f16, int n, int C, int dstC, int h,
+                         int w, float scale, cer_stream_t stream);
+/* The inverse layout change (used to hand `net` back as [1,1,64,h,w], core/update.py:116). */
+int cer_nhwc_to_nchw(const void* src, int src_f16, void* dst, int dst_f16, int n, int C, int h, int w,
+                     cer_stream_t stream);
+
+/* ---- projective_transform, matrix part (utils/projective_ops.py:16-23) ---------------------
+ * Pij[k] = K4(jj[k]) . P(jj[k]) . P(ii[k])^-1 . K4(ii[k])^-1, computed in fp64, stored fp32 row-major.
+ * poses [n,4,4] world->camera (already scaled, core/raft.py:35), intrinsics [n,3,3] already divided
+ * by the encoder stride (core/raft.py:39); ii, jj device int32 [n_pairs]. */
+int cer_projection_matrices(const float* poses, const float* intrinsics, const int* ii, const int* jj,
+                            int n_pairs, float* Pij, cer_stream_t stream);
+
+/* ---- CorrBlock.__init__ (core/corr.py:46-97), fused ----------------------------------------
+ * hypotheses (core/corr.py:56-66) + projection of (x,y,1,d) (utils/projective_ops.py:5-13,25-27) +
+ * clamp (corr.py:88) + alt_cuda_corr.forward with radius 0 (correlation_kernel.cu) + D-minor layout
+ * (corr.py:41-43,89-91), for all (ii[k], jj[k]) pairs in one launch.
+ *   feats   [n_img,h,w,64] NHWC, fp16 or fp32, ALREADY multiplied by 1/8 (cer_nchw_to_nhwc)
+ *   Pij     [n_pairs,16] (cer_projection_matrices), ii/jj device int32 [n_pairs]
+ *   disp_in [h,w] fp32; shift != 0 for stage 0 (corr.py:59-62)
+ *   origin  [h,w] fp32 out (= CorrBlock.disps_origin)
+ *   volume  out, fp32, D minor.  per_view == 0: [h*w, D] = out_scale * sum over pairs (use 1/V for the
+ *           view mean of core/update.py:103; a rank that owns a subset of views passes 1/V_total and the
+ *           partial volumes are summed across ranks).  per_view != 0: [n_pairs, h*w, D], the reference's
+ *           corr_pyramid[0] row order ((v*h+y)*w+x), each multiplied by out_scale. */
+int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+                     int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
+                     float* origin, float* volume, float out_scale, int per_view, int h, int w,
+                     cer_stream_t stream);
+
+/* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
+int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stream_t stream);
+
+/* ---- CorrBlock.__call__ (core/corr.py:102-143 + utils/bilinear_sampler.py:6-25) -------------
+ * volume [slots, h*w, D] level 0 (levels 1..L-1 are rebuilt on the fly), origin [h*w], zinv [h*w]
+ * -> out [slots, L*(2r+1), h, w] fp32 (channel = level*(2r+1) + tap).  L <= 3 needs D >= 4. */
+int cer_lookup(const float* volume, int slots, const float* origin, const float* zinv, int D,
+               float incre, int radius, int num_levels, float* out, int h, int w, cer_stream_t stream);
+
+/* Same with one zinv map per slot: zinv + slot*zinv_stride (0 = shared, what core/raft.py:99 passes). */
+int cer_lookup_strided(const float* volume, int slots, const float* origin, const float* zinv,
+                       long long zinv_stride, int D, float incre, int radius, int num_levels, float* out,
+                       int h, int w, cer_stream_t stream);
+
+/* ---- UpdateBlock (core/update.py:29-120) ---------------------------------------------------
+ * Weights are handed over as one packed blob.  cer_update_blob_bytes() gives its size;
+ * cer_pack_update_weights() fills a HOST blob from the reference's state-dict tensors (fp32, OIHW,
+ * host pointers, order below); copy it to the device once.
+ *   w[0..1]  corr_encoder.0.weight [64,33,1,1], .bias [64]
+ *   w[2..3]  corr_encoder.2.weight [64,64,3,3], .bias
+ *   w[4..5]  gru.convz.weight [64,241,3,3], .bias      w[6..7] gru.convr     w[8..9] gru.convq
+ *   w[10..11] delta0.0.weight [256,64,3,3], .bias      w[12..13] delta0.2.weight [1,256,3,3], .bias
+ *   w[14..17] delta1.* likewise
+ * Only the reference's default architecture is supported (3 levels, radius 5, 7x7 disparity
+ * encoder, aggregation ["mean"], share_corr, share_gru, per-stage delta). */
+size_t cer_update_blob_bytes(void);
+int cer_pack_update_weights(const float* const* w, void* blob_host);
+
+/* Workspace (device) for one UpdateBlock.forward at h x w. */
+size_t cer_update_workspace_bytes(int h, int w);
+
+/* One UpdateBlock.forward (core/update.py:87-120), autocast semantics (fp16 operands, fp32 accumulate,
+ * fp16 rounding where torch.cuda.amp.autocast rounds).
+ *   net   [h*w,64] fp16 NHWC, updated IN PLACE (the GRU state)      inp [h*w,64] fp16 NHWC
+ *   disp  [h*w] fp32, updated IN PLACE when `apply_delta` (core/raft.py:101)
+ *   corr  [slots,33,h,w] fp32 (CorrBlock.__call__ output); the mean over slots is taken (update.py:103)
+ *   delta [h*w] fp32 out (may be NULL)                               stage 0/1 selects delta{stage} */
+int cer_update_step(const void* blob, void* workspace, void* net, const void* inp, float* disp,
+                    const float* corr, int slots, float* delta, int apply_delta, int stage, int h, int w,
+                    cer_stream_t stream);
+
+/* ConvGRU.forward alone (core/update.py:17-25): net [h*w,64] fp16 NHWC updated in place from
+ * inputs inp [h*w,64], dn [h*w,64] (49 disparity-encoder channels + 15 zero), e [h*w,64], all fp16 NHWC. */
+int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e,
+                 int h, int w, cer_stream_t stream);
+
+/* ---- the whole hot path (core/raft.py:75-108) behind one handle ----------------------------- */
+typedef struct cer_plan cer_plan;
+
+typedef struct cer_plan_config {
+  int h, w;            /* quarter-resolution grid (H/4, W/4) */
+  int max_views;       /* largest number of source views */
+  int n_stages;        /* <= 4 */
+  int D[4];            /* hypotheses per stage (core/raft.py:77-80) */
+  double incre[4];     /* 0.0025 / N per stage (core/raft.py:81), the Python double */
+  int iters[4];        /* GRU iterations per stage */
+  int feats_f16;       /* 1: keep features in fp16 (lossless for autocast fnet output), 0: fp32 */
+  int use_graph;       /* 1: capture each stage's iteration loop in a CUDA graph */
+} cer_plan_config;
+
+/* Allocates the plan's device workspace (cudaMalloc) on the current device. */
+int cer_plan_create(const cer_plan_config* cfg, cer_plan** out);
+void cer_plan_destroy(cer_plan* plan);
+size_t cer_plan_workspace_bytes(const cer_plan* plan);
+/* Copies a HOST blob (cer_pack_update_weights) to the device; synchronous. */
+int cer_plan_set_weights(cer_plan* plan, const void* blob_host);
+
+/* Device-resident inputs.  fmaps [n_views+1,64,h,w] NCHW (fp16 if fmaps_f16 else fp32), view 0 is the
+ * reference image; net, inp [64,h,w] NCHW (same dtype flag ctx_f16); poses [n_views+1,4,4] fp32 already
+ * multiplied by scale (core/raft.py:35); intrinsics [n_views+1,3,3] fp32 already divided by 4
+ * (core/raft.py:39).  view_begin/view_end select the source views this rank builds (0..n_views for
+ * one GPU); when the range is a strict subset the partial volume of every stage is left in
+ * cer_plan_partial_volume() after cer_plan_build_stage() for the caller to all-reduce.
+ * disp_out [h,w] fp32 = disparity after the last iteration times out_scale (core/raft.py:108). */
+int cer_plan_run_device(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
+                        int ctx_f16, const float* poses, const float* intrinsics, int n_views,
+                        float out_scale, float* disp_out, cer_stream_t stream);
+
+/* Same, with HOST buffers: pinned-or-pageable host memory in, host memory out; the call copies
+ * host->device, runs, copies the disparity back and synchronises the stream (inference.py:43-57). */
+int cer_plan_run_host(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
+                      int ctx_f16, const float* poses, const float* intrinsics, int n_views,
+                      float out_scale, float* disp_out, cer_stream_t stream);
+
+/* Stage-wise API for view-sharded multi-GPU runs: prepare -> for each stage
+ * { build_stage (local views, scaled 1/total_views) ; [caller all-reduces partial_volume] ;
+ * iterate_stage } -> finish. */
+int cer_plan_prepare(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
+                     int ctx_f16, const float* poses, const float* intrinsics, int n_views,
+                     int view_begin, int view_end, cer_stream_t stream);
+int cer_plan_build_stage(cer_plan* plan, int stage, cer_stream_t stream);
+float* cer_plan_partial_volume(cer_plan* plan, int stage, size_t* n_floats);
+int cer_plan_iterate_stage(cer_plan* plan, int stage, cer_stream_t stream);
+int cer_plan_finish(cer_plan* plan, float out_scale, float* disp_out, cer_stream_t stream);
+/* Number of kernel launches issued by the last run (graph nodes count as launches). */
+long long cer_plan_last_launch_count(const cer_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CER_MVS_B200_H */

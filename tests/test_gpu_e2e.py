@@ -1,0 +1,112 @@
+"""GPU: the whole hot path (core/raft.py:75-108) -- DepthHotPath (native plan, CUDA graph) and the
+drop-in classes driven by a copy of the reference's loop -- against golden disparities of the
+reference's RAFT.forward and the oracle.  North-star bar: relative L1 on disparity <= 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+import cer_oracle as O
+from cer_mvs_b200 import synth
+from util import H, V, W, h1, rel_l1, t, w1
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # BASELINE.json north_star: "within 1e-3 relative L1 on disparity"
+
+
+def _inputs(g):
+    seed = int(g["seed"])
+    sc = synth.make_scene(H, W, V, seed=seed)
+    sd = synth.make_update_weights(seed=seed, delta_scale=float(g["delta_scale"]),
+                                   delta_bias=float(g["delta_bias"]) if "delta_bias" in g else 0.0)
+    cascade = [tuple(int(v) for v in row) for row in g["cascade"]]
+    return sc, sd, cascade
+
+
+def _hot(sc, sd, cascade, g, dtype, use_graph=True, feats_f16=True):
+    from cer_mvs_b200.hotpath import DepthHotPath
+    hp = DepthHotPath(h1, w1, max_views=V, cascade=cascade, feats_f16=feats_f16, use_graph=use_graph)
+    hp.load_update_block(sd)
+    out = hp(t(sc["fmaps"]).cuda().to(dtype), t(g["net"]).cuda().to(dtype), t(g["inp"]).cuda().to(dtype),
+             t(sc["poses"]).cuda(), t(sc["intrinsics"]).cuda(), scale=float(g["scale"]))
+    return hp, out.cpu().numpy().copy()
+
+
+@pytest.mark.parametrize("name", ["trained_like", "unscaled_oob", "drift", "scaled_pose"])
+def test_hot_path_vs_reference_fp32_golden(golden, name):
+    """CUDA path (fp16 tensor-core convs) vs the reference's fp32 CPU run (BASELINE configs[0] numerics)."""
+    g = golden("e2e_fp32_" + name)
+    sc, sd, cascade = _inputs(g)
+    _, out = _hot(sc, sd, cascade, g, torch.float32, feats_f16=False)
+    err = rel_l1(out, g["disp"])
+    print(f"{name}: rel L1 vs reference fp32 = {err:.3e}")
+    assert out.shape == g["disp"].shape
+    assert err < TOL, err
+
+
+def test_hot_path_vs_reference_autocast_golden(golden):
+    g = golden("e2e_autocast_drift")
+    sc, sd, cascade = _inputs(g)
+    _, out = _hot(sc, sd, cascade, g, torch.float16)
+    err = rel_l1(out, g["disp"])
+    print(f"rel L1 vs reference autocast = {err:.3e}")
+    assert err < TOL, err
+
+
+def test_hot_path_vs_autocast_oracle_longer(golden):
+    """16 + 16 iterations (the BASELINE metric's iteration count) against the oracle's autocast emulation."""
+    g = golden("e2e_fp32_drift")
+    sc, sd, _ = _inputs(g)
+    cascade = [(64, 64, 16), (-1, 320, 16)]
+    sd = synth.make_update_weights(seed=5, delta_scale=0.1, delta_bias=0.005)
+    _, out = _hot(sc, sd, cascade, g, torch.float16)
+    want = O.hot_path(O.to_torch_sd(sd), t(sc["fmaps"]), t(g["net"]), t(g["inp"]), t(sc["poses"]),
+                      t(sc["intrinsics"]), cascade=cascade, scale=1.0, autocast=True).numpy()
+    err = rel_l1(out, want)
+    print(f"32 iterations: rel L1 vs autocast oracle = {err:.3e}")
+    assert err < TOL, err
+
+
+def test_graph_and_eager_identical_and_host_path(golden):
+    g = golden("e2e_fp32_drift")
+    sc, sd, cascade = _inputs(g)
+    hp, a = _hot(sc, sd, cascade, g, torch.float16, use_graph=True)
+    _, b = _hot(sc, sd, cascade, g, torch.float16, use_graph=False)
+    assert np.array_equal(a, b)
+    again = hp(t(sc["fmaps"]).cuda().half(), t(g["net"]).cuda().half(), t(g["inp"]).cuda().half(),
+               t(sc["poses"]).cuda(), t(sc["intrinsics"]).cuda(), scale=1.0).cpu().numpy()
+    assert np.array_equal(a, again)            # graph replay is deterministic
+    host = hp.run_host(sc["fmaps"].astype(np.float16), g["net"].astype(np.float16), g["inp"].astype(np.float16),
+                       sc["poses"], sc["intrinsics"], scale=1.0)
+    assert np.array_equal(a, host)
+    assert hp.last_launch_count > 0
+
+
+def test_dropin_classes_in_reference_loop(golden):
+    """A transcription of core/raft.py:75-105 driving CorrBlock / UpdateBlock drop-ins, like the
+    reference's RAFT.forward would after cer_mvs_b200.install.install()."""
+    from cer_mvs_b200.corr import CorrBlock
+    from cer_mvs_b200.update import UpdateBlock
+    g = golden("e2e_fp32_drift")
+    sc, sd, cascade = _inputs(g)
+    ub = UpdateBlock(cascade=cascade, dim_net=64, dim_inp=64)
+    ub.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    ub = ub.cuda().eval()
+    fmaps = t(sc["fmaps"]).cuda().half()
+    net, inp = t(g["net"]).cuda().half(), t(g["inp"]).cuda().half()
+    poses, K = t(sc["poses"]).cuda(), t(sc["intrinsics"]).cuda().clone()
+    K[:, :, :2] /= 4
+    ii = torch.zeros(V, dtype=torch.long).cuda()
+    jj = torch.arange(1, V + 1).cuda()
+    disp = torch.zeros(1, 1, h1, w1).cuda()
+    with torch.no_grad():
+        for stage, (nIncre, incre, nIters) in enumerate(O.stage_params(cascade)):
+            corr_fn = CorrBlock(fmaps, poses, K, ii, jj, nIncre=nIncre, incre=incre, disps_input=disp.detach(),
+                                shift=stage == 0, num_levels=ub.num_levels, radius=ub.radius, test_mode=True,
+                                do_report=False)
+            for _ in range(nIters):
+                corr_frames = corr_fn(disp[:, ii])
+                net, delta = ub(net, inp, disp, corr_frames, stage)
+                disp = disp + delta.float()
+    _, hot = _hot(sc, sd, cascade, g, torch.float16)
+    assert np.array_equal(disp.cpu().numpy(), hot)            # same kernels, same order -> bit-identical
+    assert rel_l1(disp.cpu().numpy(), g["disp"]) < TOL
