@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- depth-maps/sec of the CER-MVS inference hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path (core/raft.py:75-108: 2 cost-volume builds + 16+16 GRU
+iterations) over one synthetic DTU-shaped reference image (1184x1600, 10 source views, fp16
+features; BASELINE.json configs[1]).  One process per GPU; at N > 1 every rank works on its own
+reference image (replicas, weak scaling, no data-path collective), and the view-sharded single-image
+path (one NCCL all-reduce of the partial cost volume per stage) is timed next to it.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference's algorithm
+(oracle/cer_oracle.py, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from cer_mvs_b200 import synth  # noqa: E402
+
+H, W, V = 1184, 1600, 10                  # BASELINE.json configs[1]
+CASCADE = [(64, 64, 16), (-1, 320, 16)]   # "32 iters": 16 + 16 (reference default is 8 + 8, core/raft.py:16)
+WORKLOAD = "DTU 1184x1600 (296x400 grid), 10 source views, 16+16 GRU iterations, fp16 features (BASELINE configs[1])"
+METRIC = "depth-maps/sec (DTU 1600x1184, 10 src views, 32 iters)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tensor=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference algorithm) on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(rows=24, iters=(1, 1)):
+    """Runs rows 0..rows-1 of the 296-row grid (all 400 columns, all 10 views): both volume builds and
+    iters[s] GRU iterations per stage, then extrapolates linearly in pixels and iterations to a full
+    depth map.  Returns (seconds per full depth map, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cer_oracle as O
+    h1, w1 = H // 4, W // 4
+    sc = synth.make_scene(4 * rows, W, V, seed=0)     # same cameras/columns, a band of rows
+    sd = O.to_torch_sd(synth.make_update_weights(seed=0, delta_scale=0.1, delta_bias=0.005))
+    t = torch.from_numpy
+    fm, net, inp = t(sc["fmaps"]), t(sc["net"]), t(sc["inp"])
+    poses, K = t(sc["poses"]).clone(), t(sc["intrinsics"]).clone()
+    K[:, :, :2] /= 4
+    ii, jj = [0] * V, list(range(1, V + 1))
+    disp = torch.zeros(1, 1, rows, w1)
+    t_build = t_iter = 0.0
+    n_it = 0
+    with torch.no_grad():
+        for stage, (D, incre, _) in enumerate(O.stage_params(CASCADE)):
+            t0 = time.perf_counter()
+            pyr, origin = O.build_volume(fm, poses, K, ii, jj, D, incre, disp, stage == 0)
+            t_build += time.perf_counter() - t0
+            for _ in range(iters[stage]):
+                t0 = time.perf_counter()
+                cf = O.lookup(pyr, origin, D, incre, disp[:, ii])
+                net, delta = O.update_block(sd, net, inp, disp, cf, stage, autocast=False)
+                disp = disp + delta
+                t_iter += time.perf_counter() - t0
+                n_it += 1
+    scale_px = h1 / rows
+    total_iters = sum(c[2] for c in CASCADE)
+    full = t_build * scale_px + (t_iter / n_it) * total_iters * scale_px
+    desc = (f"rows 0..{rows - 1} of {h1} x {w1} cols x {V} views: both volume builds + {iters[0]}+{iters[1]} of "
+            f"16+16 iterations, fp32, extrapolated linearly in pixels and iterations ({t_build + t_iter:.1f}s of CPU work)")
+    return full, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    for _ in range(args.warmup):
+        cpu_sample(rows=8, iters=(1, 1))
+    times = []
+    desc = ""
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        full, desc = cpu_sample(rows=args.ref_rows, iters=(1, 1))
+        times.append(full)
+    wall = time.perf_counter() - t0
+    sec = float(np.mean(times))
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "depth-maps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU port of the reference algorithm (oracle/cer_oracle.py); the "
+                   "reference's own Python cannot travel to the GPU box and its alt_cuda_corr is CUDA-only"},
+        "cpu_baseline": {"value": val, "unit": "depth-maps/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "depth-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------
+def algorithmic(px):
+    """Algorithmic work per launch of each kernel class."""
+    return {
+        "conv_gates": ("tensor", 2.0 * px * 9 * 64 * (241 + 241 + 177)),
+        "conv_q_gru": ("tensor", 2.0 * px * 9 * 64 * 64),
+        "conv_delta": ("tensor", 2.0 * px * (9 * 64 * 256 + 9 * 256)),
+        "conv_corr_enc_3x3": ("tensor", 2.0 * px * 9 * 64 * 64),
+        "corr_enc_1x1": ("tensor", 2.0 * px * 33 * 64),
+        # lookup: disp + origin + 3 windows of 12 floats read, 33 floats written = 284 B / pixel
+        "lookup": ("hbm", 284.0 * px),
+        # fused build per stage: (V+1) feature maps fp16 + disp + volume write; D averaged over the two stages
+        "volume_build": ("hbm", (V + 1) * px * 64 * 2.0 + 4.0 * px + 4.0 * px * (64 + 44) / 2),
+    }
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from cer_mvs_b200 import _lib
+    from cer_mvs_b200.hotpath import DepthHotPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (cer_mvs_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    _lib.check(_lib.lib().cer_device_check(), "device check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    h1, w1 = H // 4, W // 4
+    px = h1 * w1
+
+    sc = synth.make_scene(H, W, V, seed=rank)
+    sd = synth.make_update_weights(seed=0, delta_scale=0.1, delta_bias=0.005)
+    t = torch.from_numpy
+    h_fm = t(sc["fmaps"]).half().pin_memory()
+    h_net = t(sc["net"]).half().pin_memory()
+    h_inp = t(sc["inp"]).half().pin_memory()
+    h_out = torch.empty(1, 1, h1, w1).pin_memory()
+    d_fm, d_net, d_inp = h_fm.to(dev), h_net.to(dev), h_inp.to(dev)
+    d_poses, d_K = t(sc["poses"]).to(dev), t(sc["intrinsics"]).to(dev)
+
+    hp = DepthHotPath(h1, w1, max_views=V, cascade=CASCADE, feats_f16=True, use_graph=True)
+    hp.load_update_block(sd)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop()
+    launches = hp.last_launch_count * args.steps
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- end to end with host buffers (e2e) ----
+    for _ in range(min(args.warmup, 2)):
+        hp.run_host(h_fm, h_net, h_inp, sc["poses"], sc["intrinsics"], 1.0, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hp.run_host(h_fm, h_net, h_inp, sc["poses"], sc["intrinsics"], 1.0, out=h_out)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    h2d = h_fm.numel() * 2 + h_net.numel() * 2 + h_inp.numel() * 2 + (V + 1) * (16 + 9) * 4
+    d2h = px * 4
+    e2e = world * args.steps / e2e_s
+
+    # ---- per-kernel breakdown with CUDA events (eager), roofline of the dominant kernel ----
+    hp.set_kernel_timing(True)
+    hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+    hp.kernel_times()
+    ksteps = min(args.steps, 5)
+    for _ in range(ksteps):
+        hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+    kt = hp.kernel_times()
+    hp.set_kernel_timing(False)
+    pk = peaks()
+    alg = algorithmic(px)
+    kernels = {}
+    for k, (tot, n) in kt.items():
+        if n == 0:
+            continue
+        ent = {"ms_per_step": tot / ksteps, "launches_per_step": n / ksteps, "avg_us": 1e3 * tot / n}
+        if k in alg:
+            bound, work = alg[k]
+            ach = work / (tot / n * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+            ent.update(bound=bound, achieved=ach, frac=ach / pk[bound], unit="GB/s" if bound == "hbm" else "TFLOP/s")
+        kernels[k] = ent
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from an ncu --set full capture
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get(dom)
+    roof = {"kernel": dom, "bound": kernels[dom].get("bound"), "achieved": kernels[dom].get("achieved"),
+            "peak": pk.get(kernels[dom].get("bound", "tensor")), "unit": kernels[dom].get("unit"),
+            "frac": kernels[dom].get("frac"), "traffic": traffic, "peak_source": pk["src"],
+            "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["ms_per_step"] /
+            sum(v["ms_per_step"] for v in kernels.values())}
+
+    # ---- view-sharded single image (NCCL all-reduce of the partial volume per stage) ----
+    viewshard = None
+    if world > 1 and world <= V:
+        sc0 = sc if rank == 0 else synth.make_scene(H, W, V, seed=0)
+        f0, n0, i0 = t(sc0["fmaps"]).half().to(dev), t(sc0["net"]).half().to(dev), t(sc0["inp"]).half().to(dev)
+        p0, k0 = t(sc0["poses"]).to(dev), t(sc0["intrinsics"]).to(dev)
+        for _ in range(3):
+            hp.forward_view_sharded(f0, n0, i0, p0, k0, 1.0)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            hp.forward_view_sharded(f0, n0, i0, p0, k0, 1.0)
+        e1.record()
+        barrier()
+        vms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        viewshard = {"ms_per_depth_map": vms, "depth_maps_per_s": 1e3 / vms, "collective": "nccl all_reduce(sum) of "
+                     f"the partial volume, {px * 64 * 4 / 1e6:.1f}+{px * 44 * 4 / 1e6:.1f} MB per depth map"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        full, desc = cpu_sample(rows=args.ref_rows, iters=(1, 1))
+        cpu = {"value": 1.0 / full, "unit": "depth-maps/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": desc}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "depth-maps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: 167 MB fp16 feature maps + 30 MB volume + 110 MB update "
+                             "workspace are re-streamed every step (L2 = 126 MB)",
+                       "engine": "cer_plan, CUDA graph per cascade stage"},
+            "e2e": {"value": e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+        }
+        if viewshard:
+            line["viewshard"] = viewshard
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-rows", type=int, default=24, help="rows of the 296-row grid in one CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

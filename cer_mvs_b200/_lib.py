@@ -51,6 +51,8 @@ SIGNATURES = {
     "cer_plan_partial_volume": (c_void_p, [c_void_p, c_int, C.POINTER(c_size_t)]),
     "cer_plan_iterate_stage": (c_int, [c_void_p, c_int, c_void_p]),
     "cer_plan_finish": (c_int, [c_void_p, c_float, c_void_p, c_void_p]),
+    "cer_plan_set_kernel_timing": (c_int, [c_void_p, c_int]),
+    "cer_plan_kernel_times": (c_int, [c_void_p, C.POINTER(c_double), C.POINTER(c_ll), c_int, c_void_p]),
     "cer_plan_last_launch_count": (c_ll, [c_void_p]),
 }
 

@@ -168,10 +168,10 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   const int chunks = ceil_div(D, 8);
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
   if (feats_f16)
-    CER_LAUNCH(build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
+    CER_LAUNCH(KK_BUILD, build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
                shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
   else
-    CER_LAUNCH(build_volume_kernel<float>, grid, 256, 0, stream, (const float*)feats, Pij, ii, jj, n_pairs, disp_in,
+    CER_LAUNCH(KK_BUILD, build_volume_kernel<float>, grid, 256, 0, stream, (const float*)feats, Pij, ii, jj, n_pairs, disp_in,
                shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
   return check_launch("cer_build_volume");
 }

@@ -25,6 +25,7 @@ int check_launch(const char* what);
   do {                                                                              \
     cudaError_t e_ = (call);                                                        \
     if (e_ != cudaSuccess) {                                                        \
+      cudaGetLastError(); /* do not leave a sticky error for the host framework */  \
       cer::set_error("%s failed: %s", #call, cudaGetErrorString(e_));               \
       return (int)e_;                                                               \
     }                                                                               \
@@ -36,13 +37,25 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 constexpr int kFeatC = 64;        // dim_fmap (core/raft.py:18)
 constexpr int kNumSMs = 148;      // B200
 
-// launch counter (cer_plan_last_launch_count): every kernel launch in the library goes through LAUNCH
+// launch counter (cer_plan_last_launch_count): every kernel launch in the library goes through CER_LAUNCH
 extern thread_local long long g_launches;
+
+// Kernel classes, for the per-kernel CUDA-event timing of cer_plan_set_kernel_timing().
+enum KernelKind {
+  KK_LAYOUT = 0, KK_PROJ, KK_BUILD, KK_POOL, KK_LOOKUP, KK_CORR_DROPIN, KK_DISP_ENC, KK_CORR_ENC1, KK_CONV_E,
+  KK_CONV_GATES, KK_CONV_Q, KK_CONV_DELTA, KK_DISP_UPDATE, KK_FINISH, KK_COUNT
+};
+struct KernelTimer;                       // defined in plan.cu
+extern thread_local KernelTimer* g_timer; // non-null while a plan runs eagerly with timing enabled
+void timer_begin(int kind, cudaStream_t s);
+void timer_end(cudaStream_t s);
 
 }  // namespace cer
 
-#define CER_LAUNCH(kernel, grid, block, smem, stream, ...)            \
-  do {                                                                \
-    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
-    ++cer::g_launches;                                                \
+#define CER_LAUNCH(kind, kernel, grid, block, smem, stream, ...)                \
+  do {                                                                          \
+    if (cer::g_timer) cer::timer_begin((kind), (cudaStream_t)(stream));         \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);   \
+    if (cer::g_timer) cer::timer_end((cudaStream_t)(stream));                   \
+    ++cer::g_launches;                                                          \
   } while (0)

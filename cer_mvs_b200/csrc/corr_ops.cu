@@ -334,20 +334,20 @@ int cer_device_check(void) {
 
 int cer_corr_forward_f32(const float* fmap1, const float* fmap2, const float* coords, float* corr, int B,
                          int H1, int W1, int H2, int W2, int C, int N, int radius, cer_stream_t stream) {
-  CER_REQUIRE(fmap1 && fmap2 && coords && corr, "cer_corr_forward_f32: null pointer");
   CER_REQUIRE(B >= 0 && H1 >= 0 && W1 >= 0 && H2 > 0 && W2 > 0 && C > 0 && N >= 0 && radius >= 0,
               "cer_corr_forward_f32: bad sizes");
   const long long total = (long long)B * N * H1 * W1;
-  if (total == 0) return CER_OK;
+  if (total == 0) return CER_OK;   // empty output (pointers of empty tensors may be null)
+  CER_REQUIRE(fmap1 && fmap2 && coords && corr, "cer_corr_forward_f32: null pointer");
   const long long threads = total * 8;
   CER_REQUIRE(threads / 256 < 0x7fffffffLL, "cer_corr_forward_f32: problem too large");
   const bool vec = (C % 4 == 0) && aligned16(fmap1) && aligned16(fmap2);
   const int grid = ceil_div(threads, 256);
   if (vec)
-    CER_LAUNCH(corr_forward_dropin_kernel<true>, grid, 256, 0, stream, fmap1, fmap2, coords, corr, B, H1, W1, H2,
+    CER_LAUNCH(KK_CORR_DROPIN, corr_forward_dropin_kernel<true>, grid, 256, 0, stream, fmap1, fmap2, coords, corr, B, H1, W1, H2,
                W2, C, N, radius);
   else
-    CER_LAUNCH(corr_forward_dropin_kernel<false>, grid, 256, 0, stream, fmap1, fmap2, coords, corr, B, H1, W1, H2,
+    CER_LAUNCH(KK_CORR_DROPIN, corr_forward_dropin_kernel<false>, grid, 256, 0, stream, fmap1, fmap2, coords, corr, B, H1, W1, H2,
                W2, C, N, radius);
   return check_launch("cer_corr_forward_f32");
 }
@@ -358,13 +358,13 @@ int cer_nchw_to_nhwc_pad(const void* src, int src_f16, void* dst, int dst_f16, i
   const long long px = (long long)h * w;
   dim3 grid(ceil_div(px, 32), ceil_div(dstC, 32), n);
   if (src_f16 && dst_f16)
-    CER_LAUNCH((nchw_to_nhwc_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, dstC, px, scale);
+    CER_LAUNCH(KK_LAYOUT, (nchw_to_nhwc_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, dstC, px, scale);
   else if (src_f16 && !dst_f16)
-    CER_LAUNCH((nchw_to_nhwc_kernel<__half, float>), grid, 256, 0, stream, (const __half*)src, (float*)dst, C, dstC, px, scale);
+    CER_LAUNCH(KK_LAYOUT, (nchw_to_nhwc_kernel<__half, float>), grid, 256, 0, stream, (const __half*)src, (float*)dst, C, dstC, px, scale);
   else if (!src_f16 && dst_f16)
-    CER_LAUNCH((nchw_to_nhwc_kernel<float, __half>), grid, 256, 0, stream, (const float*)src, (__half*)dst, C, dstC, px, scale);
+    CER_LAUNCH(KK_LAYOUT, (nchw_to_nhwc_kernel<float, __half>), grid, 256, 0, stream, (const float*)src, (__half*)dst, C, dstC, px, scale);
   else
-    CER_LAUNCH((nchw_to_nhwc_kernel<float, float>), grid, 256, 0, stream, (const float*)src, (float*)dst, C, dstC, px, scale);
+    CER_LAUNCH(KK_LAYOUT, (nchw_to_nhwc_kernel<float, float>), grid, 256, 0, stream, (const float*)src, (float*)dst, C, dstC, px, scale);
   return check_launch("cer_nchw_to_nhwc");
 }
 
@@ -379,20 +379,20 @@ int cer_nhwc_to_nchw(const void* src, int src_f16, void* dst, int dst_f16, int n
   const long long px = (long long)h * w;
   dim3 grid(ceil_div(px, 32), ceil_div(C, 32), n);
   if (src_f16 && dst_f16)
-    CER_LAUNCH((nhwc_to_nchw_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, px);
+    CER_LAUNCH(KK_LAYOUT, (nhwc_to_nchw_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, px);
   else if (src_f16 && !dst_f16)
-    CER_LAUNCH((nhwc_to_nchw_kernel<__half, float>), grid, 256, 0, stream, (const __half*)src, (float*)dst, C, px);
+    CER_LAUNCH(KK_LAYOUT, (nhwc_to_nchw_kernel<__half, float>), grid, 256, 0, stream, (const __half*)src, (float*)dst, C, px);
   else if (!src_f16 && dst_f16)
-    CER_LAUNCH((nhwc_to_nchw_kernel<float, __half>), grid, 256, 0, stream, (const float*)src, (__half*)dst, C, px);
+    CER_LAUNCH(KK_LAYOUT, (nhwc_to_nchw_kernel<float, __half>), grid, 256, 0, stream, (const float*)src, (__half*)dst, C, px);
   else
-    CER_LAUNCH((nhwc_to_nchw_kernel<float, float>), grid, 256, 0, stream, (const float*)src, (float*)dst, C, px);
+    CER_LAUNCH(KK_LAYOUT, (nhwc_to_nchw_kernel<float, float>), grid, 256, 0, stream, (const float*)src, (float*)dst, C, px);
   return check_launch("cer_nhwc_to_nchw");
 }
 
 int cer_projection_matrices(const float* poses, const float* intrinsics, const int* ii, const int* jj,
                             int n_pairs, float* Pij, cer_stream_t stream) {
   CER_REQUIRE(poses && intrinsics && ii && jj && Pij && n_pairs > 0, "cer_projection_matrices: bad arguments");
-  CER_LAUNCH(projection_matrices_kernel, ceil_div(n_pairs, 32), 32, 0, stream, poses, intrinsics, ii, jj, n_pairs, Pij);
+  CER_LAUNCH(KK_PROJ, projection_matrices_kernel, ceil_div(n_pairs, 32), 32, 0, stream, poses, intrinsics, ii, jj, n_pairs, Pij);
   return check_launch("cer_projection_matrices");
 }
 
@@ -400,7 +400,7 @@ int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stre
   CER_REQUIRE(src && dst && rows >= 0 && W >= 2, "cer_pool_pairs: bad arguments");
   const long long total = rows * (W / 2);
   if (total == 0) return CER_OK;
-  CER_LAUNCH(pool_pairs_kernel, ceil_div(total, 256), 256, 0, stream, src, dst, rows, W);
+  CER_LAUNCH(KK_POOL, pool_pairs_kernel, ceil_div(total, 256), 256, 0, stream, src, dst, rows, W);
   return check_launch("cer_pool_pairs");
 }
 
@@ -417,7 +417,7 @@ int cer_lookup_strided(const float* volume, int slots, const float* origin, cons
   if (smem > 48 * 1024)
     CER_CUDA(cudaFuncSetAttribute(lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(px, kLookupPix), slots);
-  CER_LAUNCH(lookup_kernel, grid, kLookupPix, smem, stream, volume, origin, zinv, zinv_stride, D, incre, radius,
+  CER_LAUNCH(KK_LOOKUP, lookup_kernel, grid, kLookupPix, smem, stream, volume, origin, zinv, zinv_stride, D, incre, radius,
              num_levels, out, px);
   return check_launch("cer_lookup");
 }

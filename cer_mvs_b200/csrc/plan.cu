@@ -8,6 +8,45 @@
 #include "update_blob.h"
 
 namespace cer {
+
+// ---- per-kernel CUDA-event timing (eager mode only; used by bench.py for the roofline numbers) ----
+struct KernelTimer {
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<int> kinds;
+  size_t used = 0;
+  double ms[KK_COUNT] = {0};
+  long long count[KK_COUNT] = {0};
+};
+thread_local KernelTimer* g_timer = nullptr;
+
+void timer_begin(int kind, cudaStream_t s) {
+  KernelTimer* t = g_timer;
+  if (t->used + 2 > t->ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      t->ev.push_back(e);
+    }
+  }
+  t->kinds.push_back(kind);
+  cudaEventRecord(t->ev[t->used], s);
+}
+void timer_end(cudaStream_t s) {
+  KernelTimer* t = g_timer;
+  cudaEventRecord(t->ev[t->used + 1], s);
+  t->used += 2;
+}
+static void timer_collect(KernelTimer* t) {   // caller has synchronised the stream
+  for (size_t i = 0; i < t->used; i += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t->ev[i], t->ev[i + 1]);
+    t->ms[t->kinds[i / 2]] += ms;
+    t->count[t->kinds[i / 2]] += 1;
+  }
+  t->used = 0;
+  t->kinds.clear();
+}
+
 int update_step_hmma(const void* blob, void* workspace, void* net, const void* inp, float* disp, const float* corr,
                      int slots, float* delta, int apply_delta, int stage, int h, int w, cudaStream_t stream);
 int update_configure();
@@ -52,9 +91,11 @@ struct cer_plan {
   // run state
   int n_views = 0, vb = 0, ve = 0;
   bool have_weights = false;
+  cudaStream_t capture_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy one)
   cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
   long long graph_nodes[4] = {0, 0, 0, 0};
   long long launches = 0;
+  KernelTimer* timer = nullptr;   // non-null: run eagerly and time every kernel with CUDA events
 };
 
 static int plan_alloc(cer_plan* p, void** ptr, size_t bytes) {
@@ -106,6 +147,7 @@ int cer_plan_create(const cer_plan_config* cfg, cer_plan** out) {
   }
   iota_pairs_kernel<<<1, 64>>>(p->ii, p->jj, cfg->max_views);
   rc = update_configure();
+  if (!rc) rc = (int)cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking);
   if (!rc) rc = (int)cudaDeviceSynchronize();
   if (rc) {
     cer_plan_destroy(p);
@@ -119,6 +161,11 @@ void cer_plan_destroy(cer_plan* p) {
   if (!p) return;
   for (int s = 0; s < 4; ++s)
     if (p->graph[s]) cudaGraphExecDestroy(p->graph[s]);
+  if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  if (p->timer) {
+    for (cudaEvent_t e : p->timer->ev) cudaEventDestroy(e);
+    delete p->timer;
+  }
   void* ptrs[] = {p->feats, p->net, p->inp, p->disp, p->origin, p->volume, p->corr, p->Pij, p->poses,
                   p->intr,  p->ii,  p->jj,  p->ws,   p->blob,   p->stage_in};
   for (void* q : ptrs)
@@ -204,7 +251,7 @@ int cer_plan_iterate_stage(cer_plan* p, int s, cer_stream_t stream_) {
   CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_iterate_stage: bad stage");
   cudaStream_t stream = (cudaStream_t)stream_;
   if (p->cfg.iters[s] == 0) return CER_OK;
-  if (!p->cfg.use_graph) {
+  if (!p->cfg.use_graph || p->timer) {
     cer::g_launches = 0;
     int rc = issue_iterations(p, s, stream);
     p->launches += cer::g_launches;
@@ -212,10 +259,11 @@ int cer_plan_iterate_stage(cer_plan* p, int s, cer_stream_t stream_) {
   }
   if (!p->graph[s]) {
     cudaGraph_t g = nullptr;
-    CER_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    // capture on the plan's own stream (capturing records, it does not execute); replay on the caller's
+    CER_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal));
     cer::g_launches = 0;
-    int rc = issue_iterations(p, s, stream);
-    cudaError_t e = cudaStreamEndCapture(stream, &g);
+    int rc = issue_iterations(p, s, p->capture_stream);
+    cudaError_t e = cudaStreamEndCapture(p->capture_stream, &g);
     if (rc || e != cudaSuccess) {
       if (g) cudaGraphDestroy(g);
       if (!rc) {
@@ -235,7 +283,7 @@ int cer_plan_iterate_stage(cer_plan* p, int s, cer_stream_t stream_) {
 
 int cer_plan_finish(cer_plan* p, float out_scale, float* disp_out, cer_stream_t stream) {
   CER_REQUIRE(p && disp_out, "cer_plan_finish: null pointer");
-  CER_LAUNCH(scale_copy_kernel, ceil_div(p->px, 256), 256, 0, stream, p->disp, disp_out, out_scale, p->px);
+  CER_LAUNCH(KK_FINISH, scale_copy_kernel, ceil_div(p->px, 256), 256, 0, stream, p->disp, disp_out, out_scale, p->px);
   p->launches += 1;
   return check_launch("cer_plan_finish");
 }
@@ -243,13 +291,41 @@ int cer_plan_finish(cer_plan* p, float out_scale, float* disp_out, cer_stream_t 
 int cer_plan_run_device(cer_plan* p, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
                         int ctx_f16, const float* poses, const float* intrinsics, int n_views, float out_scale,
                         float* disp_out, cer_stream_t stream) {
+  CER_REQUIRE(p, "cer_plan_run_device: null plan");
+  cer::g_timer = p->timer;
   int rc = cer_plan_prepare(p, fmaps, fmaps_f16, net, inp, ctx_f16, poses, intrinsics, n_views, 0, n_views, stream);
-  if (rc) return rc;
-  for (int s = 0; s < p->cfg.n_stages; ++s) {
-    if ((rc = cer_plan_build_stage(p, s, stream))) return rc;
-    if ((rc = cer_plan_iterate_stage(p, s, stream))) return rc;
+  for (int s = 0; !rc && s < p->cfg.n_stages; ++s) {
+    rc = cer_plan_build_stage(p, s, stream);
+    if (!rc) rc = cer_plan_iterate_stage(p, s, stream);
   }
-  return cer_plan_finish(p, out_scale, disp_out, stream);
+  if (!rc) rc = cer_plan_finish(p, out_scale, disp_out, stream);
+  cer::g_timer = nullptr;
+  return rc;
+}
+
+int cer_plan_set_kernel_timing(cer_plan* p, int enable) {
+  CER_REQUIRE(p, "cer_plan_set_kernel_timing: null plan");
+  if (enable && !p->timer) p->timer = new KernelTimer();
+  if (!enable && p->timer) {
+    for (cudaEvent_t e : p->timer->ev) cudaEventDestroy(e);
+    delete p->timer;
+    p->timer = nullptr;
+  }
+  return CER_OK;
+}
+
+int cer_plan_kernel_times(cer_plan* p, double* ms_by_kind, long long* launches_by_kind, int n_kinds,
+                          cer_stream_t stream) {
+  CER_REQUIRE(p && p->timer && ms_by_kind && launches_by_kind, "cer_plan_kernel_times: timing not enabled");
+  CER_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  timer_collect(p->timer);
+  for (int k = 0; k < n_kinds && k < KK_COUNT; ++k) {
+    ms_by_kind[k] = p->timer->ms[k];
+    launches_by_kind[k] = p->timer->count[k];
+    p->timer->ms[k] = 0;
+    p->timer->count[k] = 0;
+  }
+  return CER_OK;
 }
 
 int cer_plan_run_host(cer_plan* p, const void* fmaps, int fmaps_f16, const void* net, const void* inp, int ctx_f16,

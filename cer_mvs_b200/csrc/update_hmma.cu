@@ -428,7 +428,8 @@ template <int N_TILE, int EPI>
 static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
   constexpr int smem = ConvSmem<N_TILE>::TOTAL;
   const int tiles = ((a.w + TW - 1) / TW) * ((a.h + TH - 1) / TH);
-  CER_LAUNCH((conv3x3_hmma_kernel<N_TILE, EPI>), tiles, 256, smem, stream, a);
+  constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
+  CER_LAUNCH(kind, (conv3x3_hmma_kernel<N_TILE, EPI>), tiles, 256, smem, stream, a);
   return check_launch("conv3x3_hmma");
 }
 
@@ -440,8 +441,8 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   UpdateWs ws = carve_ws(workspace, px);
   int rc;
   if ((rc = update_configure())) return rc;
-  CER_LAUNCH(disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
-  CER_LAUNCH(corr_enc1_kernel, ceil_div(px, 128), 256, 0, stream, corr, slots, (const __half*)(B + L.w1),
+  CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
+  CER_LAUNCH(KK_CORR_ENC1, corr_enc1_kernel, ceil_div(px, 128), 256, 0, stream, corr, slots, (const __half*)(B + L.w1),
              (const float*)(B + L.b1), ws.e1, px);
   if ((rc = check_launch("update prologue"))) return rc;
   ConvArgs a{};
@@ -463,7 +464,7 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   a.bias = (const float*)(B + L.bd0[stage]); a.w2 = (const float*)(B + L.wd1[stage]); a.s9 = ws.s9;
   if ((rc = launch_conv<256, EPI_DELTA>(a, stream))) return rc;
   // K6
-  CER_LAUNCH(disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, (const float*)(B + L.bd1[stage]), disp,
+  CER_LAUNCH(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, (const float*)(B + L.bd1[stage]), disp,
              delta, apply_delta, h, w);
   return check_launch("disp_update");
 }

@@ -167,6 +167,23 @@ class DepthHotPath:
                        "cer_plan_finish")
         return out
 
+    KERNEL_KINDS = ["layout", "projection", "volume_build", "pool", "lookup", "corr_dropin", "disp_encoder",
+                    "corr_enc_1x1", "conv_corr_enc_3x3", "conv_gates", "conv_q_gru", "conv_delta", "disp_update",
+                    "finish"]
+
+    def set_kernel_timing(self, enable: bool):
+        """Eager mode with CUDA events around every kernel (bench.py's per-kernel breakdown)."""
+        _lib.check(_lib.lib().cer_plan_set_kernel_timing(self._plan, int(enable)), "set_kernel_timing")
+
+    def kernel_times(self):
+        """{kernel class: (total ms, launches)} since the last call; synchronises the current stream."""
+        n = len(self.KERNEL_KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cer_plan_kernel_times(self._plan, ms, cnt, n, _lib.stream_ptr()), "kernel_times")
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.KERNEL_KINDS)}
+
     @property
     def last_launch_count(self):
         return int(_lib.lib().cer_plan_last_launch_count(self._plan))

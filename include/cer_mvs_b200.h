@@ -170,6 +170,16 @@ int cer_plan_build_stage(cer_plan* plan, int stage, cer_stream_t stream);
 float* cer_plan_partial_volume(cer_plan* plan, int stage, size_t* n_floats);
 int cer_plan_iterate_stage(cer_plan* plan, int stage, cer_stream_t stream);
 int cer_plan_finish(cer_plan* plan, float out_scale, float* disp_out, cer_stream_t stream);
+/* Per-kernel timing for roofline accounting: when enabled the plan runs eagerly (no graph) and brackets
+ * every kernel launch with CUDA events on the launching stream.  cer_plan_kernel_times() synchronises
+ * the stream, returns accumulated milliseconds and launch counts per kernel class and resets them.
+ * Classes (index): 0 layout, 1 projection, 2 volume build, 3 pool, 4 lookup, 5 corr drop-in,
+ * 6 disp encoder, 7 corr encoder 1x1, 8 conv corr-encoder 3x3, 9 conv gates, 10 conv q + GRU,
+ * 11 conv delta, 12 disp update, 13 finish. */
+#define CER_KERNEL_KINDS 14
+int cer_plan_set_kernel_timing(cer_plan* plan, int enable);
+int cer_plan_kernel_times(cer_plan* plan, double* ms_by_kind, long long* launches_by_kind, int n_kinds,
+                          cer_stream_t stream);
 /* Number of kernel launches issued by the last run (graph nodes count as launches). */
 long long cer_plan_last_launch_count(const cer_plan* plan);
 

