@@ -193,8 +193,14 @@ def run_ours(args):
     d_fm, d_net, d_inp = h_fm.to(dev), h_net.to(dev), h_inp.to(dev)
     d_poses, d_K = t(sc["poses"]).to(dev), t(sc["intrinsics"]).to(dev)
 
-    hp = DepthHotPath(h1, w1, max_views=V, cascade=CASCADE, feats_f16=True, use_graph=True)
+    hp = DepthHotPath(h1, w1, max_views=V, cascade=CASCADE, feats_f16=True, use_graph=not args.profile_step)
     hp.load_update_block(sd)
+    if args.profile_step:       # for ncu: W warm-up steps, then exactly one eager step, nothing else
+        for _ in range(args.warmup + 1):
+            hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_step": True, "launches_per_step": hp.last_launch_count}))
+        return
 
     def barrier():
         if world > 1:
@@ -323,6 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-rows", type=int, default=24, help="rows of the 296-row grid in one CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="ncu helper: warm-up + one eager step only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

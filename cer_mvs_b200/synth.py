@@ -118,14 +118,14 @@ def make_context_pre(h1, w1, dim_net: int = 64, dim_inp: int = 64, seed: int = 0
     """What ``cnet`` would emit before the tanh / relu split: [1, 1, dim_net+dim_inp, h1, w1]."""
     rs = np.random.RandomState(seed + 2000)
     pre = np.concatenate([_smooth_field(rs, dim_net, h1, w1), _smooth_field(rs, dim_inp, h1, w1)], 0)
-    return pre.astype(np.float32)[None, None]
+    return np.ascontiguousarray(pre, dtype=np.float32)[None, None]
 
 
 def make_context(h1, w1, dim_net: int = 64, dim_inp: int = 64, seed: int = 0, fp16_exact: bool = True):
     """(net, inp), each [1, 1, C, h1, w1] float32: tanh / relu of smooth fields (core/raft.py:57-60)."""
     pre = make_context_pre(h1, w1, dim_net, dim_inp, seed)[0, 0]
-    net = np.tanh(pre[:dim_net]).astype(np.float32)
-    inp = np.maximum(pre[dim_net:], 0).astype(np.float32)
+    net = np.ascontiguousarray(np.tanh(pre[:dim_net]), dtype=np.float32)
+    inp = np.ascontiguousarray(np.maximum(pre[dim_net:], 0), dtype=np.float32)
     if fp16_exact:
         net = net.astype(np.float16).astype(np.float32)
         inp = inp.astype(np.float16).astype(np.float32)
