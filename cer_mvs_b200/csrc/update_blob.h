@@ -27,6 +27,12 @@ struct BlobLayout {
   size_t bd0[2];  // f32  [256]
   size_t wd1[2];  // f32  [9][256]            delta{s}.2 (fp16-rounded values)
   size_t bd1[2];  // f32  [1]
+  // tcgen05 copies of the 3x3 weights: per (chunk, tap) one UMMA K-major no-swizzle B tile,
+  // [kgroup = 8][n = N][8 halfs]  (element (k, n) at ((k/8 * N + n) * 8 + k%8) * 2 bytes)
+  size_t t_w2;     // [1*9] tiles, N = 64
+  size_t t_wg;     // [4*9] tiles, N = 192
+  size_t t_wq;     // [1*9] tiles, N = 64
+  size_t t_wd0[2]; // [1*9] tiles, N = 256
   size_t total;
 };
 
@@ -49,6 +55,10 @@ inline BlobLayout blob_layout() {
     L.wd1[s] = take(9 * kDelta0 * 4);
     L.bd1[s] = take(4);
   }
+  L.t_w2 = take(9 * 64 * kHid * 2);
+  L.t_wg = take(4 * 9 * 64 * kGateN * 2);
+  L.t_wq = take(9 * 64 * kHid * 2);
+  for (int s = 0; s < 2; ++s) L.t_wd0[s] = take(9 * 64 * kDelta0 * 2);
   L.total = o;
   return L;
 }

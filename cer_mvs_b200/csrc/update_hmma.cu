@@ -12,16 +12,15 @@
 //   K6 disp_update     delta = 0.01 * (b + sum_t s9[p+off_t][t]); disp += delta       update.py:71,114 raft.py:101
 #include <string.h>
 
-#include "common.cuh"
-#include "update_blob.h"
+#include <stdlib.h>
+
+#include "update_common.cuh"
 
 namespace cer {
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
   const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
@@ -44,8 +43,6 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ float h_round(float v) { return __half2float(__float2half_rn(v)); }
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
 
 // ------------------------------------------------------------------------------------------
 // K0: disparity-neighbourhood encoder -> [px][64] fp16 (channels 49..63 zero)
@@ -146,23 +143,6 @@ constexpr int HALO_PX = HALO_W * HALO_H;       // 180
 constexpr int A_PITCH = 64 + 8;                // halfs per halo pixel (144 B, conflict-free ldmatrix)
 constexpr int A_BYTES = HALO_PX * A_PITCH * 2; // 25920
 constexpr int NSTAGE = 3;
-
-enum Epilogue { EPI_RELU = 0, EPI_GATES = 1, EPI_GRUOUT = 2, EPI_DELTA = 3 };
-
-struct ConvArgs {
-  const __half* src[4];
-  int n_src;
-  const __half* wpk;   // [n_src][9][64][N_TILE]
-  const float* bias;   // [N_TILE] or null
-  int h, w;
-  __half* out_h;       // EPI_RELU: [px][64]
-  __half* net;         // EPI_GATES: read; EPI_GRUOUT: read + written in place
-  __half* z;           // EPI_GATES: write; EPI_GRUOUT: read
-  __half* rnet;        // EPI_GATES: write
-  float* qx;           // EPI_GATES: write; EPI_GRUOUT: read
-  const float* w2;     // EPI_DELTA: [9][256]
-  float* s9;           // EPI_DELTA: [px][9]
-};
 
 template <int N_TILE>
 struct ConvSmem {
@@ -383,27 +363,6 @@ __global__ void __launch_bounds__(256) disp_update_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct UpdateWs {
-  __half *dn, *e1, *e, *z, *rnet;
-  float *qx, *s9;
-  size_t total;
-};
-
-static UpdateWs carve_ws(void* base, long long px) {
-  UpdateWs w{};
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return (char*)base + r; };
-  w.dn = (__half*)take(px * 64 * 2);
-  w.e1 = (__half*)take(px * 64 * 2);
-  w.e = (__half*)take(px * 64 * 2);
-  w.z = (__half*)take(px * 64 * 2);
-  w.rnet = (__half*)take(px * 64 * 2);
-  w.qx = (float*)take(px * 64 * 4);
-  w.s9 = (float*)take(px * 9 * 4);
-  w.total = o;
-  return w;
-}
-
 template <int N_TILE, int EPI>
 static int configure_conv() {
   CER_CUDA(cudaFuncSetAttribute(conv3x3_hmma_kernel<N_TILE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -411,11 +370,21 @@ static int configure_conv() {
   return CER_OK;
 }
 
+static int g_variant = -1;
+int conv_variant() {
+  if (g_variant < 0) {
+    const char* e = getenv("CER_CONV");
+    g_variant = (e && !strcmp(e, "hmma")) ? 0 : 1;
+  }
+  return g_variant;
+}
+
 // Opt in to >48 KB dynamic shared memory once per process (not capturable, so done up front).
 int update_configure() {
   static bool done = false;
   if (done) return CER_OK;
   int rc;
+  if ((rc = tc_configure())) return rc;
   if ((rc = configure_conv<64, EPI_RELU>())) return rc;
   if ((rc = configure_conv<192, EPI_GATES>())) return rc;
   if ((rc = configure_conv<64, EPI_GRUOUT>())) return rc;
@@ -425,7 +394,9 @@ int update_configure() {
 }
 
 template <int N_TILE, int EPI>
-static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
+static int launch_conv(const ConvArgs& a_in, cudaStream_t stream) {
+  if (conv_variant() == 1) return launch_conv_tc_dispatch(N_TILE, EPI, a_in, stream);
+  const ConvArgs& a = a_in;
   constexpr int smem = ConvSmem<N_TILE>::TOTAL;
   const int tiles = ((a.w + TW - 1) / TW) * ((a.h + TH - 1) / TH);
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
@@ -449,18 +420,18 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   a.h = h;
   a.w = w;
   // K2
-  a.src[0] = ws.e1; a.n_src = 1; a.wpk = (const __half*)(B + L.w2); a.bias = (const float*)(B + L.b2); a.out_h = ws.e;
+  a.src[0] = ws.e1; a.n_src = 1; a.wpk = (const __half*)(B + L.w2); a.wtc = (const __half*)(B + L.t_w2); a.bias = (const float*)(B + L.b2); a.out_h = ws.e;
   if ((rc = launch_conv<64, EPI_RELU>(a, stream))) return rc;
   // K3
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = ws.dn; a.src[3] = ws.e; a.n_src = 4;
-  a.wpk = (const __half*)(B + L.wg); a.bias = (const float*)(B + L.bg);
+  a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
   if ((rc = launch_conv<192, EPI_GATES>(a, stream))) return rc;
   // K4
-  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.bias = nullptr;
+  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;
   if ((rc = launch_conv<64, EPI_GRUOUT>(a, stream))) return rc;
   // K5
-  a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]);
+  a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]); a.wtc = (const __half*)(B + L.t_wd0[stage]);
   a.bias = (const float*)(B + L.bd0[stage]); a.w2 = (const float*)(B + L.wd1[stage]); a.s9 = ws.s9;
   if ((rc = launch_conv<256, EPI_DELTA>(a, stream))) return rc;
   // K6
@@ -530,6 +501,19 @@ int cer_pack_update_weights(const float* const* w, void* blob_host) {
       for (int t = 0; t < 9; ++t) d[t * 256 + c] = __half2float(H(w1[c * 9 + t]));
     *(float*)(B + L.bd1[s]) = b1[0];
   }
+  // tcgen05 layout: re-tile every [tap][k][n] matrix into [tap][k/8][n][k%8]
+  auto retile = [&](size_t src_off, size_t dst_off, int n_chunks, int N) {
+    const __half* src = (const __half*)(B + src_off);
+    __half* dst = (__half*)(B + dst_off);
+    for (long long st = 0; st < (long long)n_chunks * 9; ++st)
+      for (int k = 0; k < 64; ++k)
+        for (int n = 0; n < N; ++n)
+          dst[st * 64 * N + ((long long)(k / 8) * N + n) * 8 + (k % 8)] = src[st * 64 * N + (long long)k * N + n];
+  };
+  retile(L.w2, L.t_w2, 1, 64);
+  retile(L.wg, L.t_wg, 4, kGateN);
+  retile(L.wq, L.t_wq, 1, 64);
+  for (int s = 0; s < 2; ++s) retile(L.wd0[s], L.t_wd0[s], 1, kDelta0);
   // biases are rounded to fp16 by autocast as well (conv2d casts every floating argument)
   auto round_bias = [&](size_t off, int n) {
     float* b = (float*)(B + off);
@@ -545,6 +529,12 @@ int cer_pack_update_weights(const float* const* w, void* blob_host) {
   return CER_OK;
 }
 
+int cer_set_conv_variant(int variant) {
+  CER_REQUIRE(variant == 0 || variant == 1, "cer_set_conv_variant: 0 (mma.sync) or 1 (tcgen05)");
+  g_variant = variant;
+  return CER_OK;
+}
+
 int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e, int h,
                  int w, cer_stream_t stream) {
   CER_REQUIRE(blob && workspace && net && inp && dn && e && h > 0 && w > 0, "cer_gru_step: bad arguments");
@@ -556,10 +546,10 @@ int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, 
   ConvArgs a{};
   a.h = h; a.w = w;
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = (const __half*)dn; a.src[3] = (const __half*)e;
-  a.n_src = 4; a.wpk = (const __half*)(B + L.wg); a.bias = (const float*)(B + L.bg);
+  a.n_src = 4; a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
   if ((rc = launch_conv<192, EPI_GATES>(a, (cudaStream_t)stream))) return rc;
-  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.bias = nullptr;
+  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;
   return launch_conv<64, EPI_GRUOUT>(a, (cudaStream_t)stream);
 }
 

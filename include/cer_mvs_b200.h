@@ -117,6 +117,11 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     const float* corr, int slots, float* delta, int apply_delta, int stage, int h, int w,
                     cer_stream_t stream);
 
+/* Which tensor-core path the 3x3 convolutions use: 1 = tcgen05.mma + TMEM (default), 0 = mma.sync (the v1
+ * kernels, kept for A/B validation; also selectable with CER_CONV=hmma).  Takes effect for launches and
+ * graph captures issued afterwards. */
+int cer_set_conv_variant(int variant);
+
 /* ConvGRU.forward alone (core/update.py:17-25): net [h*w,64] fp16 NHWC updated in place from
  * inputs inp [h*w,64], dn [h*w,64] (49 disparity-encoder channels + 15 zero), e [h*w,64], all fp16 NHWC. */
 int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e,

@@ -10,6 +10,15 @@ from cer_mvs_b200 import synth
 from util import H, V, W, h1, rel_l1, t, w1
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["tcgen05", "hmma"], autouse=True)
+def conv_variant(request):
+    """Every test runs on both tensor-core paths: tcgen05.mma + TMEM (default) and mma.sync (v1)."""
+    from cer_mvs_b200 import _lib
+    _lib.check(_lib.lib().cer_set_conv_variant(1 if request.param == "tcgen05" else 0))
+    yield request.param
+    _lib.lib().cer_set_conv_variant(1)
 TOL = 1e-3          # BASELINE.json north_star: "within 1e-3 relative L1 on disparity"
 
 

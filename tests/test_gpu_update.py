@@ -11,6 +11,15 @@ from util import V, h1, rel_l1, t, w1
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tcgen05", "hmma"], autouse=True)
+def conv_variant(request):
+    """Every test runs on both tensor-core paths: tcgen05.mma + TMEM (default) and mma.sync (v1)."""
+    from cer_mvs_b200 import _lib
+    _lib.check(_lib.lib().cer_set_conv_variant(1 if request.param == "tcgen05" else 0))
+    yield request.param
+    _lib.lib().cer_set_conv_variant(1)
+
+
 def _ub(sd_np):
     from cer_mvs_b200.update import UpdateBlock
     ub = UpdateBlock(cascade=[(64, 64, 8), (-1, 320, 8)], dim_net=64, dim_inp=64)
