@@ -18,6 +18,8 @@ struct ConvArgs {
   const __half* wtc;   // tcgen05 weights: [n_src*9] UMMA K-major tiles [8][N][8]
   const float* bias;   // [N] or null
   int h, w;
+  const float* disp;   // tcgen05 gate conv: disparity map for the in-kernel disparity encoder
+  int dn_chunk;        // index of the chunk generated from disp (-1: every chunk is read from src[])
   __half* out_h;       // EPI_RELU: [px][64]
   __half* net;         // EPI_GATES: read; EPI_GRUOUT: read + written in place
   __half* z;           // EPI_GATES: write; EPI_GRUOUT: read

@@ -412,13 +412,15 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   UpdateWs ws = carve_ws(workspace, px);
   int rc;
   if ((rc = update_configure())) return rc;
-  CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
+  const bool tc = conv_variant() == 1;
+  if (!tc) CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
   CER_LAUNCH(KK_CORR_ENC1, corr_enc1_kernel, ceil_div(px, 128), 256, 0, stream, corr, slots, (const __half*)(B + L.w1),
              (const float*)(B + L.b1), ws.e1, px);
   if ((rc = check_launch("update prologue"))) return rc;
   ConvArgs a{};
   a.h = h;
   a.w = w;
+  a.dn_chunk = -1;
   // K2
   a.src[0] = ws.e1; a.n_src = 1; a.wpk = (const __half*)(B + L.w2); a.wtc = (const __half*)(B + L.t_w2); a.bias = (const float*)(B + L.b2); a.out_h = ws.e;
   if ((rc = launch_conv<64, EPI_RELU>(a, stream))) return rc;
@@ -426,7 +428,9 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = ws.dn; a.src[3] = ws.e; a.n_src = 4;
   a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
+  if (tc) { a.disp = disp; a.dn_chunk = 2; }      // disparity encoder generated inside the gate conv
   if ((rc = launch_conv<192, EPI_GATES>(a, stream))) return rc;
+  a.dn_chunk = -1;
   // K4
   a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;
   if ((rc = launch_conv<64, EPI_GRUOUT>(a, stream))) return rc;
@@ -544,7 +548,7 @@ int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, 
   const char* B = (const char*)blob;
   UpdateWs ws = carve_ws(workspace, (long long)h * w);
   ConvArgs a{};
-  a.h = h; a.w = w;
+  a.h = h; a.w = w; a.dn_chunk = -1;
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = (const __half*)dn; a.src[3] = (const __half*)e;
   a.n_src = 4; a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;

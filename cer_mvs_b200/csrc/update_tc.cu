@@ -1,41 +1,48 @@
-// UpdateBlock 3x3 convolutions, v2: implicit GEMM on tcgen05.mma (5th-gen tensor cores) with the
-// accumulators in TMEM.  Same math, inputs, outputs and fused epilogues as update_hmma.cu.
+// UpdateBlock 3x3 convolutions, v3: implicit GEMM on tcgen05.mma (5th-gen tensor cores), accumulators
+// in TMEM.  Same math, inputs, outputs and fused epilogues as update_hmma.cu.
 //
-// One CTA = one 16 x 16 pixel tile = two M=128 MMA tiles (16 rows x 8 columns each) that share every
-// weight tile, N = 64 / 192 / 256 output channels, K = n_src x 9 taps x 64 channels.
+// Persistent CTAs (one per SM) walk over 16 x 8 pixel tiles (M = 128), N = 64 / 192 / 256 output
+// channels, K = n_src x 9 taps x 64 channels; the TMEM accumulator is double-buffered so the epilogue
+// of tile t overlaps the MMAs of tile t+1.  Warp roles (256 threads):
 //
-//   warps 0-3  A producers: per 64-channel chunk the 18 x 18 halo tile is brought in with 16-byte
-//              cp.async (zero fill outside the image = the conv padding) in the UMMA K-major
-//              no-swizzle layout [k-group 8][halo pixel 324][8 halfs]; a 3x3 tap is then just a shifted
-//              start address of the same tile (LBO = 324*16 B between k-groups, SBO = 18*16 B between
-//              image rows = 8-row core-matrix groups).  Afterwards the same warps run the epilogue:
-//              tcgen05.ld gives every thread all N channels of one pixel.
-//   warp 4     B producer: one elected lane streams the pre-tiled weights of each (chunk, tap) with
-//              cp.async.bulk (TMA 1-D) into an NB-stage ring; also owns the TMEM allocation.
-//   warp 5     MMA issuer: one elected lane, 4 (k16) x 2 (M tiles) tcgen05.mma per (chunk, tap),
-//              tcgen05.commit hands smem stages back to the producers and the accumulators to the epilogue.
+//   warps 0-3  epilogue: tcgen05.ld gives every thread all N channels of one pixel (TMEM lane = pixel);
+//              bias / sigmoid / tanh / GRU blend / delta dots, NHWC stores; then releases the accumulator.
+//   warp 4     MMA issuer: one elected lane, 4 (k16) tcgen05.mma per (chunk, tap); tcgen05.commit hands
+//              smem stages back to the producers and accumulators to the epilogue.  Owns the TMEM allocation.
+//   warp 5     B producer: one elected lane streams the pre-tiled weights of each (chunk, tap) with
+//              cp.async.bulk (TMA 1-D) into a ring; for N = 64 all 9 taps stay resident for the whole kernel.
+//   warps 6-7  A producers: per 64-channel chunk the 18 x 10 halo tile is brought in with 16-byte cp.async
+//              (zero fill outside the image = the conv padding) in the UMMA K-major no-swizzle layout
+//              [k-group 8][halo pixel 180][8 halfs]; a 3x3 tap is then just a shifted start address of the
+//              same tile (LBO = 180*16 B between k-groups, SBO = 10*16 B between image rows = 8-row
+//              core-matrix groups).  The disparity-encoder chunk of the gate conv (core/update.py:80-85,97)
+//              is computed here straight from disp instead of being read from HBM.
 #include "update_common.cuh"
 
 namespace cer {
 
-constexpr int TC_TH = 16, TC_TW = 16;
+constexpr int TC_TH = 16, TC_TW = 8;            // one M = 128 tile
 constexpr int TC_HW = TC_TW + 2, TC_HH = TC_TH + 2;
-constexpr int TC_HPX = TC_HW * TC_HH;          // 324 halo pixels
+constexpr int TC_HPX = TC_HW * TC_HH;          // 180 halo pixels
 constexpr int TC_A_LBO = TC_HPX * 16;          // bytes between the two 8-channel groups of one K=16 slice
 constexpr int TC_A_SBO = TC_HW * 16;           // bytes between 8-row groups (= image rows of the M tile)
-constexpr int TC_A_BYTES = 8 * TC_A_LBO;       // one 64-channel chunk: 41 472 B
-constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = 8 * TC_A_LBO;       // one 64-channel chunk: 23 040 B
+constexpr int TC_THREADS = 256;
+constexpr int TC_NA = 3;                       // A ring depth (chunks)
+constexpr int TC_PROD = 64;                    // A producer threads
+constexpr int TC_DT_H = TC_HH + 6, TC_DT_W = TC_HW + 6;   // disparity tile for the 7x7 encoder: 24 x 16
 
 template <int N>
 struct TcCfg {
-  static constexpr int NB = (N == 256) ? 3 : 4;
+  static constexpr bool RESIDENT = (N == 64);                 // all 9 weight tiles stay in smem
+  static constexpr int NB = RESIDENT ? 9 : ((N == 256) ? 3 : 4);
   static constexpr int B_BYTES = 64 * N * 2;
-  static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256 ? 256 : 512);
-  static constexpr int OFF_B = 2 * TC_A_BYTES;
+  static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256 ? 256 : 512);   // 2 accumulator stages
+  static constexpr int OFF_B = TC_NA * TC_A_BYTES;
   static constexpr int OFF_EXTRA = OFF_B + NB * B_BYTES;                  // DELTA: w2 [9][256] f32 + bias [256] f32
-  static constexpr int EXTRA_BYTES = (N == 256) ? (9 * 256 + 256) * 4 : 0;
+  static constexpr int EXTRA_BYTES = (N == 256) ? (9 * 256 + 256) * 4 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
   static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
-  static constexpr int NUM_BAR = 5 + 2 * NB;
+  static constexpr int NUM_BAR = 2 * TC_NA + 2 * NB + 4;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
@@ -108,6 +115,12 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  // 1 - 2/(e^{2x}+1): abs error ~1e-7, far below the fp16 rounding that follows; saturates cleanly
+  return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
+}
+
 __device__ __forceinline__ void st_half32(__half* dst, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -143,29 +156,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sA = s0, sB = s0 + C::OFF_B, sBar = s0 + C::OFF_BAR;
-  // barrier slots
   auto bar_a_full = [&](int i) { return sBar + 8 * i; };
-  auto bar_a_empty = [&](int i) { return sBar + 8 * (2 + i); };
-  auto bar_b_full = [&](int i) { return sBar + 8 * (4 + i); };
-  auto bar_b_empty = [&](int i) { return sBar + 8 * (4 + C::NB + i); };
-  const uint32_t bar_acc = sBar + 8 * (4 + 2 * C::NB);
+  auto bar_a_empty = [&](int i) { return sBar + 8 * (TC_NA + i); };
+  auto bar_b_full = [&](int i) { return sBar + 8 * (2 * TC_NA + i); };
+  auto bar_b_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + C::NB + i); };
+  auto bar_acc_full = [&](int i) { return sBar + 8 * (2 * TC_NA + 2 * C::NB + i); };
+  auto bar_acc_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + 2 * C::NB + 2 + i); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_x = (a.w + TC_TW - 1) / TC_TW;
-  const int x0 = (blockIdx.x % tiles_x) * TC_TW, y0 = (blockIdx.x / tiles_x) * TC_TH;
-  const int n_steps = a.n_src * 9;
+  const int n_tiles = tiles_x * ((a.h + TC_TH - 1) / TC_TH);
+  const int n_src = a.n_src;
+  // Every CTA walks the (chunk, tap) sum in its own rotated order so that the 148 SMs do not all pull the
+  // same weight tile out of L2 at the same moment (the accumulation order is free).
+  const int rot_tap = blockIdx.x % 9, rot_chunk = (blockIdx.x / 9) % n_src;
 
   if (tid == 0) {
-    mbar_init(bar_a_full(0), 128);
-    mbar_init(bar_a_full(1), 128);
-    mbar_init(bar_a_empty(0), 1);
-    mbar_init(bar_a_empty(1), 1);
+    for (int i = 0; i < TC_NA; ++i) {
+      mbar_init(bar_a_full(i), TC_PROD);
+      mbar_init(bar_a_empty(i), 1);
+    }
     for (int i = 0; i < C::NB; ++i) {
       mbar_init(bar_b_full(i), 1);
       mbar_init(bar_b_empty(i), 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_acc_full(i), 1);
+      mbar_init(bar_acc_empty(i), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -183,85 +202,157 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ================= A producers =================
-    for (int c = 0; c < a.n_src; ++c) {
-      const int buf = c & 1;
-      mbar_wait(bar_a_empty(buf), ((c >> 1) & 1) ^ 1);
-      const __half* src = a.src[c];
-      const uint32_t dst0 = sA + buf * TC_A_BYTES;
-      for (int i = tid; i < TC_HPX * 8; i += 128) {
-        const int hp = i >> 3, g = i & 7;
-        const int yy = y0 - 1 + hp / TC_HW, xx = x0 - 1 + hp % TC_HW;
-        const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
-        const __half* gp = src + ((long long)(ok ? yy : 0) * a.w + (ok ? xx : 0)) * 64 + g * 8;
-        cp_async16_zfill(dst0 + g * TC_A_LBO + hp * 16, gp, ok);
+  if (warp >= 6) {
+    // ================= A producers (64 threads) =================
+    const int pt = tid - 6 * 32;
+    int seq = 0;           // chunk sequence number over all tiles of this CTA
+    int pending = -1;      // stage whose loads were issued but not yet published
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
+      for (int ci = 0; ci < n_src; ++ci, ++seq) {
+        const int c = (ci + rot_chunk) % n_src;
+        const int st = seq % TC_NA;
+        mbar_wait(bar_a_empty(st), ((seq / TC_NA) & 1) ^ 1);
+        const uint32_t dst0 = sA + st * TC_A_BYTES;
+        if (c == a.dn_chunk) {
+          // disparity-neighbourhood encoder: channel k = 100 * (disp(y+k/7-3, x+k%7-3) - disp(y, x)), zero padded.
+          // Stage the 24 x 16 disparity tile once, then one thread per halo pixel writes its 8 k-groups.
+          float* sD = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
+          asm volatile("bar.sync 1, 64;" ::: "memory");           // previous tile's readers are done
+          for (int i = pt; i < TC_DT_H * TC_DT_W; i += TC_PROD) {
+            const int yy = y0 - 4 + i / TC_DT_W, xx = x0 - 4 + i % TC_DT_W;
+            sD[i] = (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) ? __ldg(a.disp + (long long)yy * a.w + xx) : 0.f;
+          }
+          asm volatile("bar.sync 1, 64;" ::: "memory");
+          for (int hp = pt; hp < TC_HPX; hp += TC_PROD) {
+            const int hy = hp / TC_HW, hx = hp % TC_HW;
+            const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
+            const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
+            const float* win = sD + hy * TC_DT_W + hx;             // window origin = (hy+3-3, hx+3-3)
+            const float ctr = win[3 * TC_DT_W + 3];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              __align__(16) __half v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int k = g * 8 + e;                           // compile-time after unrolling
+                float val = 0.f;
+                if (k < kDispEnc) val = __fmul_rn(100.f, __fsub_rn(win[(k / 7) * TC_DT_W + (k % 7)], ctr));
+                v[e] = __float2half_rn(ok ? val : 0.f);
+              }
+              *reinterpret_cast<uint4*>(smem + (dst0 - s0) + g * TC_A_LBO + hp * 16) = *reinterpret_cast<const uint4*>(v);
+            }
+          }
+        } else {
+          const __half* src = a.src[c];
+          for (int i = pt; i < TC_HPX * 8; i += TC_PROD) {
+            const int hp = i >> 3, g = i & 7;
+            const int yy = y0 - 1 + hp / TC_HW, xx = x0 - 1 + hp % TC_HW;
+            const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
+            const __half* gp = src + ((long long)(ok ? yy : 0) * a.w + (ok ? xx : 0)) * 64 + g * 8;
+            cp_async16_zfill(dst0 + g * TC_A_LBO + hp * 16, gp, ok);
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (pending >= 0) {   // publish the previous chunk while this one is in flight
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(bar_a_full(pending));
+        }
+        pending = st;
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (MMA) reads
-      mbar_arrive(bar_a_full(buf));
     }
-  } else if (warp == 4) {
+    if (pending >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_a_full(pending));
+    }
+  } else if (warp == 5) {
     // ================= B producer =================
     if (lane == 0) {
       const char* wsrc = reinterpret_cast<const char*>(a.wtc);
-      for (int s = 0; s < n_steps; ++s) {
-        const int st = s % C::NB;
-        mbar_wait(bar_b_empty(st), ((s / C::NB) & 1) ^ 1);
-        mbar_expect_tx(bar_b_full(st), C::B_BYTES);
-        bulk_g2s(sB + st * C::B_BYTES, wsrc + (size_t)s * C::B_BYTES, C::B_BYTES, bar_b_full(st));
+      if (C::RESIDENT) {
+        for (int s = 0; s < 9; ++s) {
+          mbar_expect_tx(bar_b_full(s), C::B_BYTES);
+          bulk_g2s(sB + s * C::B_BYTES, wsrc + (size_t)s * C::B_BYTES, C::B_BYTES, bar_b_full(s));
+        }
+      } else {
+        int seq = 0;
+        const int n_steps = n_src * 9;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          for (int si = 0; si < n_steps; ++si, ++seq) {
+            const int s = ((si / 9 + rot_chunk) % n_src) * 9 + (si % 9 + rot_tap) % 9;
+            const int st = seq % C::NB;
+            mbar_wait(bar_b_empty(st), ((seq / C::NB) & 1) ^ 1);
+            mbar_expect_tx(bar_b_full(st), C::B_BYTES);
+            bulk_g2s(sB + st * C::B_BYTES, wsrc + (size_t)s * C::B_BYTES, C::B_BYTES, bar_b_full(st));
+          }
+        }
       }
     }
-  } else {
+  } else if (warp == 4) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(128, N);
-      for (int s = 0; s < n_steps; ++s) {
-        const int chunk = s / 9, tap = s % 9, buf = chunk & 1, st = s % C::NB;
-        if (tap == 0) mbar_wait(bar_a_full(buf), (chunk >> 1) & 1);
-        mbar_wait(bar_b_full(st), (s / C::NB) & 1);
+      int aseq = 0, bseq = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        mbar_wait(bar_acc_empty(as), ((t >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const int ky = tap / 3, kx = tap % 3;
-        const uint32_t a0 = sA + buf * TC_A_BYTES + (ky * TC_HW + kx) * 16;
-        const uint32_t b0 = sB + st * C::B_BYTES;
+        const uint32_t d_tmem = tmem_base + as * N;
+        for (int c = 0; c < n_src; ++c, ++aseq) {
+          const int ast = aseq % TC_NA;
+          mbar_wait(bar_a_full(ast), (aseq / TC_NA) & 1);
+          for (int ti = 0; ti < 9; ++ti, ++bseq) {
+            const int tap = C::RESIDENT ? ti : (ti + rot_tap) % 9;
+            int bst;
+            if (C::RESIDENT) {
+              bst = tap;
+              if (t == 0) mbar_wait(bar_b_full(bst), 0);
+            } else {
+              bst = bseq % C::NB;
+              mbar_wait(bar_b_full(bst), (bseq / C::NB) & 1);
+            }
+            tc_fence_after();
+            const int ky = tap / 3, kx = tap % 3;
+            const uint32_t a0 = sA + ast * TC_A_BYTES + (ky * TC_HW + kx) * 16;
+            const uint32_t b0 = sB + bst * C::B_BYTES;
 #pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) {
-          const uint64_t bd = umma_desc(b0 + 2 * k16 * (N * 16), N * 16, 128);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t ad = umma_desc(a0 + 2 * k16 * TC_A_LBO + j * 8 * 16, TC_A_LBO, TC_A_SBO);
-            tc_mma_f16(tmem_base + j * N, ad, bd, idesc, (s > 0 || k16 > 0) ? 1u : 0u);
+            for (int k16 = 0; k16 < 4; ++k16) {
+              const uint64_t ad = umma_desc(a0 + 2 * k16 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
+              const uint64_t bd = umma_desc(b0 + 2 * k16 * (N * 16), N * 16, 128);
+              tc_mma_f16(d_tmem, ad, bd, idesc, (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u);
+            }
+            if (!C::RESIDENT) tc_commit(bar_b_empty(bst));   // stage free once these MMAs have read it
           }
+          tc_commit(bar_a_empty(ast));
         }
-        tc_commit(bar_b_empty(st));                 // smem stage free once these MMAs have read it
-        if (tap == 8) tc_commit(bar_a_empty(buf));
+        tc_commit(bar_acc_full(as));                          // accumulator complete
       }
-      tc_commit(bar_acc);                           // accumulators complete
     }
-  }
-
-  if (warp < 4) {
-    // ================= epilogue: thread = one pixel of each M tile, all N channels =================
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
+  } else {
+    // ================= epilogue: thread = one pixel, all N channels =================
     const int m = warp * 32 + lane;                 // row of the M tile = TMEM lane
     const int r = m >> 3, cc = m & 7;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-      const int yy = y0 + r, xx = x0 + j * 8 + cc;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int as = t & 1;
+      const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
+      mbar_wait(bar_acc_full(as), (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * N;
+      const int yy = y0 + r, xx = x0 + cc;
       const bool ok = yy < a.h && xx < a.w;
       const long long p = ok ? (long long)yy * a.w + xx : 0;
       float t9[9];
       if (EPI == EPI_DELTA) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) t9[t] = 0.f;
+        for (int q = 0; q < 9; ++q) t9[q] = 0.f;
       }
 #pragma unroll 1
       for (int cb = 0; cb < N / 32; ++cb) {
         uint32_t raw[32];
-        tc_ld32(lane_addr + j * N + cb * 32, raw);     // warp-collective: executed by every lane
+        tc_ld32(lane_addr + cb * 32, raw);          // warp-collective: executed by every lane
         float v[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
@@ -275,14 +366,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           for (int e = 0; e < 32; ++e) v[e] += __ldg(a.bias + n0 + e);
           if (n0 < 64) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = sigmoid_f(h_round(v[e]));
+            for (int e = 0; e < 32; ++e) v[e] = fast_sigmoid(h_round(v[e]));
             if (ok) st_half32(a.z + p * 64 + n0, v);
           } else if (n0 < 128) {
             if (ok) {
               float nt[32];
               ld_half32(a.net + p * 64 + (n0 - 64), nt);
 #pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = h_round(sigmoid_f(h_round(v[e]))) * nt[e];
+              for (int e = 0; e < 32; ++e) v[e] = h_round(fast_sigmoid(h_round(v[e]))) * nt[e];
               st_half32(a.rnet + p * 64 + (n0 - 64), v);
             }
           } else if (ok) {
@@ -303,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
             }
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              const float qv = h_round(tanhf(h_round(v[e])));
+              const float qv = h_round(fast_tanh(h_round(v[e])));
               v[e] = h_round(h_round(h_round(1.f - zz[e]) * nt[e]) + h_round(zz[e] * qv));
             }
             st_half32(a.net + p * 64 + n0, v);
@@ -313,17 +404,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = fmaxf(h_round(v[e] + ex[9 * 256 + n0 + e]), 0.f);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            float acc = t9[t];
+          for (int q = 0; q < 9; ++q) {
+            float acc = t9[q];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) acc = fmaf(v[e], ex[t * 256 + n0 + e], acc);
-            t9[t] = acc;
+            for (int e = 0; e < 32; ++e) acc = fmaf(v[e], ex[q * 256 + n0 + e], acc);
+            t9[q] = acc;
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty(as));               // accumulator stage may be overwritten
       if (EPI == EPI_DELTA && ok) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) a.s9[p * 9 + t] = t9[t];
+        for (int q = 0; q < 9; ++q) a.s9[p * 9 + q] = t9[q];
       }
     }
   }
@@ -356,8 +449,9 @@ int tc_configure() {
 template <int N, int EPI>
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = ((a.w + TC_TW - 1) / TC_TW) * ((a.h + TC_TH - 1) / TC_TH);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
-  CER_LAUNCH(kind, (conv3x3_tc_kernel<N, EPI>), tiles, TC_THREADS, TcCfg<N>::TOTAL, stream, a);
+  CER_LAUNCH(kind, (conv3x3_tc_kernel<N, EPI>), grid, TC_THREADS, TcCfg<N>::TOTAL, stream, a);
   return check_launch("conv3x3_tc");
 }
 
