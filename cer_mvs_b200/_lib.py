@@ -27,6 +27,7 @@ SIGNATURES = {
     "cer_projection_matrices": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "cer_build_volume": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                  c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p]),
+    "cer_set_build_variant": (c_int, [c_int]),
     "cer_pool_pairs": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "cer_lookup": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_int,
                            c_int, c_void_p]),

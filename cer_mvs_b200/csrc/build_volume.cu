@@ -9,6 +9,9 @@
 // = 4 full 128-byte lines (fp16) -- and accumulates slice dots weighted by the bilinear weights.
 // A 7-shuffle butterfly leaves the full dot of sample d0+L in lane L, which adds it to its
 // view-sum accumulator and finally stores 8 consecutive hypotheses (32 B) per group.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cer {
@@ -16,27 +19,60 @@ namespace cer {
 constexpr int kMaxPairs = 64;
 constexpr int kChunksPerBlock = 2;  // hypothesis chunks (of 8) handled by one block in sequence
 
+// 8 channels of one pixel and their dot product with another pixel's 8 channels.
 template <typename T>
-struct FeatSlice;  // 8 channels of one pixel
+struct FeatSlice;
+
+// fp16 features: Blackwell's mixed-precision FMA (PTX fma.rn.f32.f16 -> SASS FHFMA) multiplies two fp16
+// values exactly and accumulates in fp32 -- the same result as fmaf(float(a), float(b), c) without the
+// 64 conversions per corner row.
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {
+  float r;
+  asm("{\n .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n fma.rn.f32.f16 %0, al, bl, %3;\n}"
+      : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
+  float r;
+  asm("{\n .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n fma.rn.f32.f16 %0, ah, bh, %3;\n}"
+      : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
 
 template <>
 struct FeatSlice<__half> {
-  static __device__ __forceinline__ void load(const __half* p, float (&f)[8]) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  uint4 v;
+  __device__ __forceinline__ void load(const __half* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ float dot(const FeatSlice& o) const {
+    float d = fhfma_lo(v.x, o.v.x, 0.f);
+    d = fhfma_hi(v.x, o.v.x, d);
+    d = fhfma_lo(v.y, o.v.y, d);
+    d = fhfma_hi(v.y, o.v.y, d);
+    d = fhfma_lo(v.z, o.v.z, d);
+    d = fhfma_hi(v.z, o.v.z, d);
+    d = fhfma_lo(v.w, o.v.w, d);
+    d = fhfma_hi(v.w, o.v.w, d);
+    return d;
   }
 };
 
 template <>
 struct FeatSlice<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ float dot(const FeatSlice& o) const {
+    float d = a.x * o.a.x;
+    d = fmaf(a.y, o.a.y, d);
+    d = fmaf(a.z, o.a.z, d);
+    d = fmaf(a.w, o.a.w, d);
+    d = fmaf(b.x, o.b.x, d);
+    d = fmaf(b.y, o.b.y, d);
+    d = fmaf(b.z, o.b.z, d);
+    d = fmaf(b.w, o.b.w, d);
+    return d;
   }
 };
 
@@ -70,7 +106,7 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
 
   const long long img_stride = px * kFeatC;
   int cached_ref = -1;
-  float f1[8];
+  FeatSlice<T> f1;
 
   const int chunk0 = blockIdx.y * kChunksPerBlock;
   for (int ch = chunk0; ch < chunk0 + kChunksPerBlock; ++ch) {
@@ -83,7 +119,7 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
     for (int k = 0; k < n_pairs; ++k) {
       const int ri = sI[k];
       if (ri != cached_ref) {  // block-uniform
-        FeatSlice<T>::load(feats + ri * img_stride + p * kFeatC + lane * 8, f1);
+        f1.load(feats + ri * img_stride + p * kFeatC + lane * 8);
         cached_ref = ri;
       }
       const T* img2 = feats + sJ[k] * img_stride + lane * 8;
@@ -97,33 +133,33 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
       v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
       const float fu = floorf(u), fv = floorf(v);
       const float my_dx = u - fu, my_dy = v - fv;
-      const int my_ix = (int)fu, my_iy = (int)fv;
+      const int ix = (int)fu, iy = (int)fv;
+      // the owner lane resolves the four corners once: element offset of the pixel row, or -1 outside fmap2
+      int my_o[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int yy = iy + (c >> 1), xx = ix + (c & 1);
+        my_o[c] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? (yy * w + xx) * kFeatC : -1;
+      }
 
       float part[8];
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int ix = __shfl_sync(0xffffffffu, my_ix, s, 8);
-        const int iy = __shfl_sync(0xffffffffu, my_iy, s, 8);
+        const int o0 = __shfl_sync(0xffffffffu, my_o[0], s, 8);
+        const int o1 = __shfl_sync(0xffffffffu, my_o[1], s, 8);
+        const int o2 = __shfl_sync(0xffffffffu, my_o[2], s, 8);
+        const int o3 = __shfl_sync(0xffffffffu, my_o[3], s, 8);
         const float dx = __shfl_sync(0xffffffffu, my_dx, s, 8);
         const float dy = __shfl_sync(0xffffffffu, my_dy, s, 8);
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int yy = iy + (c >> 1), xx = ix + (c & 1);
-          if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-            float f2[8];
-            FeatSlice<T>::load(img2 + ((long long)yy * w + xx) * kFeatC, f2);
-            float dot = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dot = fmaf(f1[e], f2[e], dot);
-            const float wy = (c >> 1) ? dy : 1.f - dy;
-            const float wx = (c & 1) ? dx : 1.f - dx;
-            sum += (dot * wy) * wx;
-          } else if (dx != dx || dy != dy) {
-            sum = dx + dy;  // NaN coordinates poison the output like the reference (0 * NaN)
-          }
-        }
-        part[s] = sum;
+        FeatSlice<T> f2;
+        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+        if (o0 >= 0) { f2.load(img2 + o0); d00 = f1.dot(f2); }
+        if (o1 >= 0) { f2.load(img2 + o1); d01 = f1.dot(f2); }
+        if (o2 >= 0) { f2.load(img2 + o2); d10 = f1.dot(f2); }
+        if (o3 >= 0) { f2.load(img2 + o3); d11 = f1.dot(f2); }
+        // (dot * wy) * wx per corner (correlation_kernel.cu:97-100); NaN coordinates give NaN like the reference
+        const float wy0 = 1.f - dy, wx0 = 1.f - dx;
+        part[s] = ((d00 * wy0) * wx0 + (d01 * wy0) * dx) + ((d10 * dy) * wx0 + (d11 * dy) * dx);
       }
       // butterfly: lane L ends with the group-wide total of sample L
       float k4[4], k2[2];
@@ -154,7 +190,27 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
 
 }  // namespace cer
 
+namespace cer {
+int build_volume_tc(const void* feats, const float* Pij, const int* ii, const int* jj, int n_pairs,
+                    const float* disp_in, int shift, int D, float incre, float lo_origin, float* origin,
+                    float* volume, float out_scale, int per_view, int h, int w, cudaStream_t stream);
+static int g_build_variant = -1;
+static int build_variant() {
+  if (g_build_variant < 0) {
+    const char* e = getenv("CER_BUILD");
+    g_build_variant = (e && !strcmp(e, "tc")) ? 1 : 0;
+  }
+  return g_build_variant;
+}
+}  // namespace cer
+
 using namespace cer;
+
+extern "C" int cer_set_build_variant(int variant) {
+  CER_REQUIRE(variant == 0 || variant == 1, "cer_set_build_variant: 0 (FHFMA gather kernel) or 1 (tcgen05 gather kernel)");
+  g_build_variant = variant;
+  return CER_OK;
+}
 
 extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
                                 int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
@@ -164,6 +220,10 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   CER_REQUIRE(n_pairs > 0 && n_pairs <= kMaxPairs, "cer_build_volume: n_pairs must be 1..%d", kMaxPairs);
   CER_REQUIRE(D > 0 && h > 0 && w > 0, "cer_build_volume: bad sizes");
   CER_REQUIRE(aligned16(feats), "cer_build_volume: feats must be 16-byte aligned");
+  // fp16 features: dot products on tcgen05 (build_volume_tc.cu); a 128-entry tile must span <= 4 pixels
+  if (feats_f16 && D >= 43 && D <= 4096 && build_variant() == 1)
+    return build_volume_tc(feats, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale,
+                           per_view, h, w, (cudaStream_t)stream);
   const long long px = (long long)h * w;
   const int chunks = ceil_div(D, 8);
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
