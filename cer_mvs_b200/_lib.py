@@ -47,6 +47,9 @@ SIGNATURES = {
                                     c_float, c_void_p, c_void_p]),
     "cer_plan_run_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                   c_float, c_void_p, c_void_p]),
+    "cer_plan_submit_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                     c_float, c_void_p, c_void_p]),
+    "cer_plan_wait_host": (c_int, [c_void_p]),
     "cer_plan_prepare": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_void_p]),
     "cer_plan_build_stage": (c_int, [c_void_p, c_int, c_void_p]),

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "lookup_common.cuh"
 
 namespace cer {
 
@@ -241,15 +242,6 @@ __global__ void pool_pairs_kernel(const float* __restrict__ src, float* __restri
 // ------------------------------------------------------------------------------------------
 constexpr int kLookupPix = 128;
 
-__device__ __forceinline__ float pyr_value(const float* row, int lvl, int i, int D) {
-  // value i of pyramid level lvl (floor pooling); caller guarantees 0 <= i < (D >> lvl)
-  if (lvl == 0) return row[i];
-  if (lvl == 1) return (row[2 * i] + row[2 * i + 1]) * 0.5f;
-  const float a = (row[4 * i] + row[4 * i + 1]) * 0.5f;
-  const float b = (row[4 * i + 2] + row[4 * i + 3]) * 0.5f;
-  return (a + b) * 0.5f;
-}
-
 __global__ void __launch_bounds__(kLookupPix) lookup_kernel(
     const float* __restrict__ volume, const float* __restrict__ origin, const float* __restrict__ zinv,
     long long zinv_stride, int D, float incre, int radius, int num_levels, float* __restrict__ out,
@@ -278,32 +270,12 @@ __global__ void __launch_bounds__(kLookupPix) lookup_kernel(
   const float* row = rows + threadIdx.x * pitch;
   const float z = __ldg(zinv + slot * zinv_stride + p);
   const float o = __ldg(origin + p);
-  // coords = max((zinv - origin) / incre + D//2, 0)   (core/corr.py:107)
-  const float c = fmaxf(__fadd_rn(__fdiv_rn(__fsub_rn(z, o), incre), (float)(D / 2)), 0.f);
+  const float c = lookup_coord(z, o, incre, D);
   const int taps = 2 * radius + 1;
   float* o_ptr = out + (long long)slot * num_levels * taps * px + p;
-  for (int lvl = 0; lvl < num_levels; ++lvl) {
-    const int Wl = D >> lvl;
-    const float cl = c / (float)(1 << lvl);
-    const float wm1 = (float)(Wl - 1);
-    for (int j = -radius; j <= radius; ++j) {
-      const float x0 = __fadd_rn((float)j, cl);                                   // corr.py:129
-      const float xn = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, x0), wm1), 1.f);        // bilinear_sampler.py:12
-      const float xp = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), wm1);        // grid_sample unnormalize
-      const float fl = floorf(xp);
-      const float w1 = xp - fl;
-      const float w0 = (fl + 1.f) - xp;
-      float v = 0.f;
-      // zero padding: taps outside [0, Wl) contribute nothing; huge |xp| is out on both sides
-      if (fl >= -1.f && fl < (float)Wl) {
-        const int i0 = (int)fl;
-        const float v0 = (i0 >= 0) ? pyr_value(row, lvl, i0, D) : 0.f;
-        const float v1 = (i0 + 1 < Wl) ? pyr_value(row, lvl, i0 + 1, D) : 0.f;
-        v = v0 * w0 + v1 * w1;
-      }
-      o_ptr[(long long)(lvl * taps + (j + radius)) * px] = v;
-    }
-  }
+  for (int lvl = 0; lvl < num_levels; ++lvl)
+    for (int j = -radius; j <= radius; ++j)
+      o_ptr[(long long)(lvl * taps + (j + radius)) * px] = lookup_tap(row, D, lvl, j, c);
 }
 
 }  // namespace cer

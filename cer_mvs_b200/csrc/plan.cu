@@ -50,6 +50,10 @@ static void timer_collect(KernelTimer* t) {   // caller has synchronised the str
 int update_step_hmma(const void* blob, void* workspace, void* net, const void* inp, float* disp, const float* corr,
                      int slots, float* delta, int apply_delta, int stage, int h, int w, cudaStream_t stream);
 int update_configure();
+int update_iteration_fused(const void* blob, void* workspace, void* net, const void* inp, float* disp,
+                           const float* volume, const float* origin, int D, float incre, int apply_prev, int stage,
+                           int h, int w, cudaStream_t stream);
+int update_apply_delta(const void* blob, void* workspace, float* disp, int stage, int h, int w, cudaStream_t stream);
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, float s, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,6 +91,14 @@ struct cer_plan {
   void* blob = nullptr;
   void* stage_in = nullptr;   // host-path staging of NCHW inputs
   size_t stage_in_bytes = 0;
+  // pipelined host path (cer_plan_submit_host / cer_plan_wait_host): two staging sets, copies on a private stream
+  void* pipe_in[2] = {nullptr, nullptr};
+  size_t pipe_in_bytes[2] = {0, 0};
+  float* pipe_cam[2] = {nullptr, nullptr};     // poses + intrinsics
+  float* pipe_out[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr, out_stream = nullptr;   // H2D and D2H on separate streams (both overlap compute)
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  long long submitted = 0, waited = 0;
   size_t total_bytes = 0;
   // run state
   int n_views = 0, vb = 0, ve = 0;
@@ -162,6 +174,16 @@ void cer_plan_destroy(cer_plan* p) {
   for (int s = 0; s < 4; ++s)
     if (p->graph[s]) cudaGraphExecDestroy(p->graph[s]);
   if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  if (p->out_stream) cudaStreamDestroy(p->out_stream);
+  for (int b = 0; b < 2; ++b) {
+    if (p->pipe_in[b]) cudaFree(p->pipe_in[b]);
+    if (p->pipe_cam[b]) cudaFree(p->pipe_cam[b]);
+    if (p->pipe_out[b]) cudaFree(p->pipe_out[b]);
+    if (p->ev_h2d[b]) cudaEventDestroy(p->ev_h2d[b]);
+    if (p->ev_compute[b]) cudaEventDestroy(p->ev_compute[b]);
+    if (p->ev_out[b]) cudaEventDestroy(p->ev_out[b]);
+  }
   if (p->timer) {
     for (cudaEvent_t e : p->timer->ev) cudaEventDestroy(e);
     delete p->timer;
@@ -238,13 +260,13 @@ static int issue_iterations(cer_plan* p, int s, cudaStream_t stream) {
   const int D = p->cfg.D[s];
   const float incre = (float)p->cfg.incre[s];
   for (int it = 0; it < p->cfg.iters[s]; ++it) {
-    int rc = cer_lookup(p->volume, 1, p->origin, p->disp, D, incre, 5, 3, p->corr, p->cfg.h, p->cfg.w, stream);
-    if (rc) return rc;
-    rc = update_step_hmma(p->blob, p->ws, p->net, p->inp, p->disp, p->corr, 1, nullptr, 1, s, p->cfg.h, p->cfg.w,
-                          stream);
+    // lookup of the current disparity fused with the corr encoder; the delta of the previous iteration is
+    // applied inside the same kernel (core/raft.py:99-101)
+    int rc = update_iteration_fused(p->blob, p->ws, p->net, p->inp, p->disp, p->volume, p->origin, D, incre,
+                                    it > 0, s, p->cfg.h, p->cfg.w, stream);
     if (rc) return rc;
   }
-  return CER_OK;
+  return update_apply_delta(p->blob, p->ws, p->disp, s, p->cfg.h, p->cfg.w, stream);
 }
 
 int cer_plan_iterate_stage(cer_plan* p, int s, cer_stream_t stream_) {
@@ -359,6 +381,80 @@ int cer_plan_run_host(cer_plan* p, const void* fmaps, int fmaps_f16, const void*
   if (rc) return rc;
   CER_CUDA(cudaMemcpyAsync(disp_out, d_out, px * 4, cudaMemcpyDeviceToHost, stream));
   CER_CUDA(cudaStreamSynchronize(stream));
+  return CER_OK;
+}
+
+// ---- pipelined host path: the H2D copy of job i+1 and the D2H copy of job i overlap the kernels of job i ----
+int cer_plan_submit_host(cer_plan* p, const void* fmaps, int fmaps_f16, const void* net, const void* inp, int ctx_f16,
+                         const float* poses, const float* intrinsics, int n_views, float out_scale,
+                         float* disp_out_host, cer_stream_t stream_) {
+  CER_REQUIRE(p && fmaps && net && inp && poses && intrinsics && disp_out_host, "cer_plan_submit_host: null pointer");
+  CER_REQUIRE(n_views >= 1 && n_views <= p->cfg.max_views, "cer_plan_submit_host: bad n_views");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (p->submitted - p->waited >= 2) {
+    int rc = cer_plan_wait_host(p);
+    if (rc) return rc;
+  }
+  const int b = (int)(p->submitted & 1);
+  const long long px = p->px;
+  const size_t fm_bytes = (size_t)(n_views + 1) * 64 * px * (fmaps_f16 ? 2 : 4);
+  const size_t ctx_bytes = (size_t)64 * px * (ctx_f16 ? 2 : 4);
+  const size_t need = align256(fm_bytes) + 2 * align256(ctx_bytes);
+  if (!p->copy_stream) {
+    CER_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    CER_CUDA(cudaStreamCreateWithFlags(&p->out_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CER_CUDA(cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
+      CER_CUDA(cudaEventCreateWithFlags(&p->ev_compute[i], cudaEventDisableTiming));
+      CER_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+      CER_CUDA(cudaMalloc((void**)&p->pipe_cam[i], (p->cfg.max_views + 1) * 25 * 4));
+      CER_CUDA(cudaMalloc((void**)&p->pipe_out[i], px * 4));
+    }
+  }
+  if (need > p->pipe_in_bytes[b]) {
+    CER_CUDA(cudaStreamSynchronize(p->copy_stream));
+    CER_CUDA(cudaStreamSynchronize(p->out_stream));
+    CER_CUDA(cudaStreamSynchronize(stream));
+    if (p->pipe_in[b]) cudaFree(p->pipe_in[b]);
+    p->pipe_in[b] = nullptr;
+    p->pipe_in_bytes[b] = 0;
+    CER_CUDA(cudaMalloc(&p->pipe_in[b], need));
+    p->pipe_in_bytes[b] = need;
+  }
+  char* d_fm = (char*)p->pipe_in[b];
+  char* d_net = d_fm + align256(fm_bytes);
+  char* d_inp = d_net + align256(ctx_bytes);
+  float* d_pose = p->pipe_cam[b];
+  float* d_intr = d_pose + (p->cfg.max_views + 1) * 16;
+  // copy stream: staging set b is free once the job that used it two submits ago has been computed
+  if (p->submitted >= 2) CER_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_compute[b], 0));
+  CER_CUDA(cudaMemcpyAsync(d_fm, fmaps, fm_bytes, cudaMemcpyHostToDevice, p->copy_stream));
+  CER_CUDA(cudaMemcpyAsync(d_net, net, ctx_bytes, cudaMemcpyHostToDevice, p->copy_stream));
+  CER_CUDA(cudaMemcpyAsync(d_inp, inp, ctx_bytes, cudaMemcpyHostToDevice, p->copy_stream));
+  CER_CUDA(cudaMemcpyAsync(d_pose, poses, (n_views + 1) * 16 * 4, cudaMemcpyHostToDevice, p->copy_stream));
+  CER_CUDA(cudaMemcpyAsync(d_intr, intrinsics, (n_views + 1) * 9 * 4, cudaMemcpyHostToDevice, p->copy_stream));
+  CER_CUDA(cudaEventRecord(p->ev_h2d[b], p->copy_stream));
+  // compute stream
+  CER_CUDA(cudaStreamWaitEvent(stream, p->ev_h2d[b], 0));
+  if (p->submitted >= 2) CER_CUDA(cudaStreamWaitEvent(stream, p->ev_out[b], 0));   // pipe_out[b] has been read back
+  int rc = cer_plan_run_device(p, d_fm, fmaps_f16, d_net, d_inp, ctx_f16, d_pose, d_intr, n_views, out_scale,
+                               p->pipe_out[b], stream);
+  if (rc) return rc;
+  CER_CUDA(cudaEventRecord(p->ev_compute[b], stream));
+  // result back on its own stream: holds up neither the next job's kernels nor its H2D copy
+  CER_CUDA(cudaStreamWaitEvent(p->out_stream, p->ev_compute[b], 0));
+  CER_CUDA(cudaMemcpyAsync(disp_out_host, p->pipe_out[b], px * 4, cudaMemcpyDeviceToHost, p->out_stream));
+  CER_CUDA(cudaEventRecord(p->ev_out[b], p->out_stream));
+  p->submitted += 1;
+  return CER_OK;
+}
+
+int cer_plan_wait_host(cer_plan* p) {
+  CER_REQUIRE(p, "cer_plan_wait_host: null plan");
+  if (p->waited >= p->submitted) return CER_OK;
+  const int b = (int)(p->waited & 1);
+  CER_CUDA(cudaEventSynchronize(p->ev_out[b]));
+  p->waited += 1;
   return CER_OK;
 }
 

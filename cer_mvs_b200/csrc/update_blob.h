@@ -33,6 +33,10 @@ struct BlobLayout {
   size_t t_wg;     // [4*9] tiles, N = 192
   size_t t_wq;     // [1*9] tiles, N = 64
   size_t t_wd0[2]; // [1*9] tiles, N = 256
+  // CTA-pair (cta_group::2) copies: per (chunk, tap) [half 2][kgroup 8][n N/2][8 halfs] so that each CTA's half of
+  // the output channels is one contiguous bulk copy
+  size_t p_wg;     // [4*9] tiles, N = 192
+  size_t p_wd0[2]; // [1*9] tiles, N = 256
   size_t total;
 };
 
@@ -59,6 +63,8 @@ inline BlobLayout blob_layout() {
   L.t_wg = take(4 * 9 * 64 * kGateN * 2);
   L.t_wq = take(9 * 64 * kHid * 2);
   for (int s = 0; s < 2; ++s) L.t_wd0[s] = take(9 * 64 * kDelta0 * 2);
+  L.p_wg = take(4 * 9 * 64 * kGateN * 2);
+  for (int s = 0; s < 2; ++s) L.p_wd0[s] = take(9 * 64 * kDelta0 * 2);
   L.total = o;
   return L;
 }

@@ -16,6 +16,7 @@ struct ConvArgs {
   int n_src;
   const __half* wpk;   // HMMA weights [n_src][9][64][N]
   const __half* wtc;   // tcgen05 weights: [n_src*9] UMMA K-major tiles [8][N][8]
+  const __half* wtc2;  // CTA-pair tcgen05 weights: [n_src*9] tiles [2][8][N/2][8]
   const float* bias;   // [N] or null
   int h, w;
   const float* disp;   // tcgen05 gate conv: disparity map for the in-kernel disparity encoder
@@ -26,7 +27,7 @@ struct ConvArgs {
   __half* rnet;        // EPI_GATES: write
   float* qx;           // EPI_GATES: write; EPI_GRUOUT: read
   const float* w2;     // EPI_DELTA: [9][256]
-  float* s9;           // EPI_DELTA: [px][9]
+  float* s9;           // EPI_DELTA: [px][2][9] partial dots of the second delta conv
 };
 
 struct UpdateWs {
@@ -45,7 +46,7 @@ inline UpdateWs carve_ws(void* base, long long px) {
   w.z = (__half*)take(px * 64 * 2);
   w.rnet = (__half*)take(px * 64 * 2);
   w.qx = (float*)take(px * 64 * 4);
-  w.s9 = (float*)take(px * 9 * 4);
+  w.s9 = (float*)take(px * 18 * 4);   // [px][2 column halves][9 taps] (the mma.sync path fills half 0 only)
   w.total = o;
   return w;
 }

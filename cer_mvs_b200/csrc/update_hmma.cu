@@ -14,6 +14,7 @@
 
 #include <stdlib.h>
 
+#include "lookup_common.cuh"
 #include "update_common.cuh"
 
 namespace cer {
@@ -132,6 +133,124 @@ __global__ void __launch_bounds__(256) corr_enc1_kernel(const float* __restrict_
       *reinterpret_cast<__half2*>(e1 + p * 64 + n) = __floats2half2_rn(v0, v1);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// KA (plan only): [disp += delta of the previous iteration] + pyramid lookup + e1 = relu(conv1x1(corr)).
+// Fuses K6 of iteration i-1, CorrBlock.__call__ and K1 of iteration i: the 33 correlation planes never
+// touch HBM.  Block = 128 pixels; the level-0 volume rows are staged in shared memory (coalesced), every
+// thread pair produces the 33 taps of one pixel as the fp16 A row of the 1x1-conv MMA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lookup_enc1_kernel(
+    const float* __restrict__ volume, const float* __restrict__ origin, float* __restrict__ disp,
+    const float* __restrict__ s9, int parts, const float* __restrict__ bd1, int apply_prev, int D, float incre,
+    const __half* __restrict__ w1, const float* __restrict__ b1, __half* __restrict__ e1, int h, int w) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  __half* sA = reinterpret_cast<__half*>(fsm);                          // [128][kA1Pitch]
+  __half* sW = sA + 128 * kA1Pitch;                                     // [48][kW1Pitch]
+  float* sC = reinterpret_cast<float*>(sW + kCorrK * kW1Pitch);         // [128] lookup coordinate
+  float* rows = sC + 128;                                               // [128][D + 1]
+  const long long px = (long long)h * w;
+  const long long p0 = (long long)blockIdx.x * 128;
+  const int npix = (int)min((long long)128, px - p0);
+  const int tid = threadIdx.x;
+  const int pitch = D + 1;
+  // stage volume rows
+  const float* vsrc = volume + p0 * D;
+  if ((D & 3) == 0) {
+    const int nvec = npix * D / 4;
+    for (int i = tid; i < nvec; i += 256) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(vsrc) + i);
+      const int e = i * 4;
+      float* d = rows + (e / D) * pitch + (e % D);
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int i = tid; i < npix * D; i += 256) rows[(i / D) * pitch + (i % D)] = __ldg(vsrc + i);
+  }
+  for (int i = tid; i < kCorrK * kHid / 8; i += 256) {
+    const int k = i / (kHid / 8), c = i % (kHid / 8);
+    *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
+  }
+  // disparity of this block's pixels (after applying the pending delta) -> lookup coordinate
+  if (tid < 128) {
+    float c = 0.f;
+    if (tid < npix) {
+      const long long p = p0 + tid;
+      float dsp = disp[p];
+      if (apply_prev) {     // K6 of the previous iteration: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t]))
+        const int x = (int)(p % w), y = (int)(p / w);
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
+            s += (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
+          }
+        }
+        dsp += h_round(0.01f * h_round(s + __ldg(bd1)));
+        disp[p] = dsp;
+      }
+      c = lookup_coord(dsp, __ldg(origin + p), incre, D);
+    }
+    sC[tid] = c;
+  }
+  __syncthreads();
+  {  // lookup: thread pair per pixel, 24 of the 48 A columns each (33 real taps, the rest zero); the tap loop is
+     // fully unrolled so level and offset are compile-time and the independent taps overlap
+    const int pl = tid & 127, half = tid >> 7;
+    const float* row = rows + pl * pitch;
+    const float c = sC[pl];
+    const bool live = pl < npix;
+    __half* arow = sA + pl * kA1Pitch;
+    if (half == 0) {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) arow[k] = __float2half_rn(live ? lookup_tap(row, D, k / 11, k % 11 - 5, c) : 0.f);
+    } else {
+#pragma unroll
+      for (int k = 24; k < 48; ++k)
+        arow[k] = __float2half_rn((live && k < kCorrPlanes) ? lookup_tap(row, D, k / 11, k % 11 - 5, c) : 0.f);
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const uint32_t aBase = smem_u32(sA) + ((warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kA1Pitch + 8 * (lane >> 4)) * 2;
+  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * kW1Pitch + 8 * (lane >> 4)) * 2;
+#pragma unroll
+  for (int k16 = 0; k16 < kCorrK / 16; ++k16) {
+    uint32_t a[4];
+    ldmatrix_x4(a, aBase + k16 * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t b[4];
+      ldmatrix_x4_trans(b, bBase + (k16 * 16 * kW1Pitch + j * 16) * 2);
+      mma16816(acc[2 * j], a, b[0], b[1]);
+      mma16816(acc[2 * j + 1], a, b[2], b[3]);
+    }
+  }
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const long long p = p0 + warp * 16 + g + 8 * half;
+    if (p >= px) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = j * 8 + q * 2;
+      const float v0 = fmaxf(h_round(acc[j][2 * half] + __ldg(b1 + n)), 0.f);
+      const float v1 = fmaxf(h_round(acc[j][2 * half + 1] + __ldg(b1 + n + 1)), 0.f);
+      *reinterpret_cast<__half2*>(e1 + p * 64 + n) = __floats2half2_rn(v0, v1);
+    }
+  }
+}
+
+static size_t lookup_enc1_smem(int D) {
+  return (size_t)128 * kA1Pitch * 2 + (size_t)kCorrK * kW1Pitch * 2 + 128 * 4 + (size_t)128 * (D + 1) * 4;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -290,7 +409,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) 
     for (int i = tid; i < 128 * 9; i += 256) {
       const int pl = i / 9, t = i % 9;
       const int yy = y0 + pl / TW, xx = x0 + pl % TW;
-      if (yy < a.h && xx < a.w) a.s9[((long long)yy * a.w + xx) * 9 + t] = sS9[i];
+      if (yy < a.h && xx < a.w) a.s9[((long long)yy * a.w + xx) * 18 + t] = sS9[i];
     }
     return;
   }
@@ -342,9 +461,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) 
 // ------------------------------------------------------------------------------------------
 // K6: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t])); disp += delta
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) disp_update_kernel(const float* __restrict__ s9, const float* __restrict__ bd1,
-                                                         float* __restrict__ disp, float* __restrict__ delta,
-                                                         int apply, int h, int w) {
+__global__ void __launch_bounds__(256) disp_update_kernel(const float* __restrict__ s9, int parts,
+                                                         const float* __restrict__ bd1, float* __restrict__ disp,
+                                                         float* __restrict__ delta, int apply, int h, int w) {
   const long long px = (long long)h * w;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= px) return;
@@ -353,7 +472,10 @@ __global__ void __launch_bounds__(256) disp_update_kernel(const float* __restric
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-    if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += __ldg(s9 + ((long long)yy * w + xx) * 9 + t);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
+      s += (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
+    }
   }
   const float d = h_round(0.01f * h_round(s + __ldg(bd1)));
   if (delta) delta[p] = d;
@@ -370,11 +492,13 @@ static int configure_conv() {
   return CER_OK;
 }
 
+void tc_set_cg2(int enabled);
 static int g_variant = -1;
 int conv_variant() {
   if (g_variant < 0) {
     const char* e = getenv("CER_CONV");
     g_variant = (e && !strcmp(e, "hmma")) ? 0 : 1;
+    if (e && !strcmp(e, "tc2")) tc_set_cg2(1);
   }
   return g_variant;
 }
@@ -389,6 +513,8 @@ int update_configure() {
   if ((rc = configure_conv<192, EPI_GATES>())) return rc;
   if ((rc = configure_conv<64, EPI_GRUOUT>())) return rc;
   if ((rc = configure_conv<256, EPI_DELTA>())) return rc;
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_smem(256)));
   done = true;
   return CER_OK;
 }
@@ -426,7 +552,7 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   if ((rc = launch_conv<64, EPI_RELU>(a, stream))) return rc;
   // K3
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = ws.dn; a.src[3] = ws.e; a.n_src = 4;
-  a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.bias = (const float*)(B + L.bg);
+  a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.wtc2 = (const __half*)(B + L.p_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
   if (tc) { a.disp = disp; a.dn_chunk = 2; }      // disparity encoder generated inside the gate conv
   if ((rc = launch_conv<192, EPI_GATES>(a, stream))) return rc;
@@ -435,12 +561,65 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;
   if ((rc = launch_conv<64, EPI_GRUOUT>(a, stream))) return rc;
   // K5
-  a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]); a.wtc = (const __half*)(B + L.t_wd0[stage]);
+  a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]); a.wtc = (const __half*)(B + L.t_wd0[stage]); a.wtc2 = (const __half*)(B + L.p_wd0[stage]);
   a.bias = (const float*)(B + L.bd0[stage]); a.w2 = (const float*)(B + L.wd1[stage]); a.s9 = ws.s9;
   if ((rc = launch_conv<256, EPI_DELTA>(a, stream))) return rc;
   // K6
-  CER_LAUNCH(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, (const float*)(B + L.bd1[stage]), disp,
-             delta, apply_delta, h, w);
+  CER_LAUNCH(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, tc ? 2 : 1,
+             (const float*)(B + L.bd1[stage]), disp, delta, apply_delta, h, w);
+  return check_launch("disp_update");
+}
+
+// One GRU iteration of the plan (core/raft.py:96-101): KA (apply pending delta, lookup, 1x1) + K2..K5.
+// The delta of THIS iteration stays pending in ws.s9 (applied by the next KA or by update_apply_delta).
+int update_iteration_fused(const void* blob, void* workspace, void* net, const void* inp, float* disp,
+                           const float* volume, const float* origin, int D, float incre, int apply_prev, int stage,
+                           int h, int w, cudaStream_t stream) {
+  const BlobLayout L = blob_layout();
+  const char* B = (const char*)blob;
+  const long long px = (long long)h * w;
+  UpdateWs ws = carve_ws(workspace, px);
+  int rc;
+  if ((rc = update_configure())) return rc;
+  if (D > 256) {
+    set_error("update_iteration_fused: D > 256 unsupported");
+    return CER_ERR_INVALID;
+  }
+  const bool tc = conv_variant() == 1;
+  CER_LAUNCH(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, 128), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
+             ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre, (const __half*)(B + L.w1),
+             (const float*)(B + L.b1), ws.e1, h, w);
+  if (!tc) CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
+  if ((rc = check_launch("lookup_enc1"))) return rc;
+  ConvArgs a{};
+  a.h = h;
+  a.w = w;
+  a.dn_chunk = -1;
+  a.src[0] = ws.e1; a.n_src = 1; a.wpk = (const __half*)(B + L.w2); a.wtc = (const __half*)(B + L.t_w2);
+  a.bias = (const float*)(B + L.b2); a.out_h = ws.e;
+  if ((rc = launch_conv<64, EPI_RELU>(a, stream))) return rc;
+  a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = ws.dn; a.src[3] = ws.e; a.n_src = 4;
+  a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.wtc2 = (const __half*)(B + L.p_wg); a.bias = (const float*)(B + L.bg);
+  a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
+  if (tc) { a.disp = disp; a.dn_chunk = 2; }
+  if ((rc = launch_conv<192, EPI_GATES>(a, stream))) return rc;
+  a.dn_chunk = -1;
+  a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;
+  if ((rc = launch_conv<64, EPI_GRUOUT>(a, stream))) return rc;
+  a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]);
+  a.wtc = (const __half*)(B + L.t_wd0[stage]); a.wtc2 = (const __half*)(B + L.p_wd0[stage]); a.bias = (const float*)(B + L.bd0[stage]);
+  a.w2 = (const float*)(B + L.wd1[stage]); a.s9 = ws.s9;
+  return launch_conv<256, EPI_DELTA>(a, stream);
+}
+
+// K6 on its own: apply the pending delta (after the last iteration of a stage).
+int update_apply_delta(const void* blob, void* workspace, float* disp, int stage, int h, int w, cudaStream_t stream) {
+  const BlobLayout L = blob_layout();
+  const char* B = (const char*)blob;
+  const long long px = (long long)h * w;
+  UpdateWs ws = carve_ws(workspace, px);
+  CER_LAUNCH(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, conv_variant() == 1 ? 2 : 1,
+             (const float*)(B + L.bd1[stage]), disp, (float*)nullptr, 1, h, w);
   return check_launch("disp_update");
 }
 
@@ -518,6 +697,19 @@ int cer_pack_update_weights(const float* const* w, void* blob_host) {
   retile(L.wg, L.t_wg, 4, kGateN);
   retile(L.wq, L.t_wq, 1, 64);
   for (int s = 0; s < 2; ++s) retile(L.wd0[s], L.t_wd0[s], 1, kDelta0);
+  // CTA-pair layout: [tap][half][k/8][n % (N/2)][k%8]
+  auto retile_pair = [&](size_t src_off, size_t dst_off, int n_chunks, int N) {
+    const __half* src = (const __half*)(B + src_off);
+    __half* dst = (__half*)(B + dst_off);
+    const int NL = N / 2;
+    for (long long st = 0; st < (long long)n_chunks * 9; ++st)
+      for (int k = 0; k < 64; ++k)
+        for (int n = 0; n < N; ++n)
+          dst[st * 64 * N + (((long long)(n / NL) * 8 + k / 8) * NL + n % NL) * 8 + (k % 8)] =
+              src[st * 64 * N + (long long)k * N + n];
+  };
+  retile_pair(L.wg, L.p_wg, 4, kGateN);
+  for (int s = 0; s < 2; ++s) retile_pair(L.wd0[s], L.p_wd0[s], 1, kDelta0);
   // biases are rounded to fp16 by autocast as well (conv2d casts every floating argument)
   auto round_bias = [&](size_t off, int n) {
     float* b = (float*)(B + off);
@@ -534,8 +726,10 @@ int cer_pack_update_weights(const float* const* w, void* blob_host) {
 }
 
 int cer_set_conv_variant(int variant) {
-  CER_REQUIRE(variant == 0 || variant == 1, "cer_set_conv_variant: 0 (mma.sync) or 1 (tcgen05)");
-  g_variant = variant;
+  CER_REQUIRE(variant >= 0 && variant <= 2,
+              "cer_set_conv_variant: 0 (mma.sync), 1 (tcgen05, CTA pairs for N >= 192) or 2 (tcgen05, single CTA, default)");
+  g_variant = variant == 0 ? 0 : 1;
+  tc_set_cg2(variant == 1);
   return CER_OK;
 }
 
@@ -550,7 +744,7 @@ int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, 
   ConvArgs a{};
   a.h = h; a.w = w; a.dn_chunk = -1;
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = (const __half*)dn; a.src[3] = (const __half*)e;
-  a.n_src = 4; a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.bias = (const float*)(B + L.bg);
+  a.n_src = 4; a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.wtc2 = (const __half*)(B + L.p_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
   if ((rc = launch_conv<192, EPI_GATES>(a, (cudaStream_t)stream))) return rc;
   a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;

@@ -28,22 +28,27 @@ constexpr int TC_HPX = TC_HW * TC_HH;          // 180 halo pixels
 constexpr int TC_A_LBO = TC_HPX * 16;          // bytes between the two 8-channel groups of one K=16 slice
 constexpr int TC_A_SBO = TC_HW * 16;           // bytes between 8-row groups (= image rows of the M tile)
 constexpr int TC_A_BYTES = 8 * TC_A_LBO;       // one 64-channel chunk: 23 040 B
-constexpr int TC_THREADS = 256;
 constexpr int TC_NA = 3;                       // A ring depth (chunks)
-constexpr int TC_PROD = 64;                    // A producer threads
+constexpr int TC_PROD = 96;                    // A producer threads (80 active: one per (halo column, k-group))
+constexpr int TC_W_MMA = 8, TC_W_BPROD = 9, TC_W_APROD = 10;   // warp roles; warps 0-7 are the epilogue
+constexpr int TC_THREADS = (TC_W_APROD + TC_PROD / 32) * 32;    // 416
 constexpr int TC_DT_H = TC_HH + 6, TC_DT_W = TC_HW + 6;   // disparity tile for the 7x7 encoder: 24 x 16
 
-template <int N>
+// CG2: the CTA pair of a 2-CTA cluster runs one M=256 tcgen05.mma.cta_group::2 per step: each CTA supplies its own
+// 128 pixel rows of A and HALF of the weight tile (N/2 output channels), which halves the weight traffic from L2
+// and the shared-memory operand reads per SM -- the limiter of the 1-CTA form.
+template <int N, bool CG2 = false>
 struct TcCfg {
   static constexpr bool RESIDENT = (N == 64);                 // all 9 weight tiles stay in smem
-  static constexpr int NB = RESIDENT ? 9 : ((N == 256) ? 3 : 4);
-  static constexpr int B_BYTES = 64 * N * 2;
+  static constexpr int NB = RESIDENT ? 9 : (CG2 ? 8 : ((N == 256) ? 4 : 6));   // weight ring depth
+  static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
+  static constexpr int B_BYTES = 64 * NLOC * 2;
   static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256 ? 256 : 512);   // 2 accumulator stages
   static constexpr int OFF_B = TC_NA * TC_A_BYTES;
   static constexpr int OFF_EXTRA = OFF_B + NB * B_BYTES;                  // DELTA: w2 [9][256] f32 + bias [256] f32
   static constexpr int EXTRA_BYTES = (N == 256) ? (9 * 256 + 256) * 4 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
   static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
-  static constexpr int NUM_BAR = 2 * TC_NA + 2 * NB + 4;
+  static constexpr int NUM_BAR = 2 * TC_NA + 3 * NB + 4;      // a_full/empty, b_full/empty/peer_full, acc_full/empty
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
@@ -83,9 +88,10 @@ __device__ __forceinline__ void ld_half32(const __half* src, float (&v)[32]) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int N, int EPI>
+template <int N, int EPI, bool CG2>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArgs a) {
-  using C = TcCfg<N>;
+  using C = TcCfg<N, CG2>;
+  static_assert(!(CG2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sA = s0, sB = s0 + C::OFF_B, sBar = s0 + C::OFF_BAR;
@@ -93,54 +99,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   auto bar_a_empty = [&](int i) { return sBar + 8 * (TC_NA + i); };
   auto bar_b_full = [&](int i) { return sBar + 8 * (2 * TC_NA + i); };
   auto bar_b_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + C::NB + i); };
-  auto bar_acc_full = [&](int i) { return sBar + 8 * (2 * TC_NA + 2 * C::NB + i); };
-  auto bar_acc_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + 2 * C::NB + 2 + i); };
+  auto bar_b_peer = [&](int i) { return sBar + 8 * (2 * TC_NA + 2 * C::NB + i); };      // CG2, leader only
+  auto bar_acc_full = [&](int i) { return sBar + 8 * (2 * TC_NA + 3 * C::NB + i); };
+  auto bar_acc_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + 3 * C::NB + 2 + i); };
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_x = (a.w + TC_TW - 1) / TC_TW;
   const int n_tiles = tiles_x * ((a.h + TC_TH - 1) / TC_TH);
+  // every CTA runs the same number of tile iterations (a CTA pair must stay in lock step); surplus tile indices
+  // lie below the image: all loads zero-fill, nothing is stored
+  const int n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
   const int n_src = a.n_src;
-  // Every CTA walks the (chunk, tap) sum in its own rotated order so that the 148 SMs do not all pull the
+  // Every CTA (pair) walks the (chunk, tap) sum in its own rotated order so that the 148 SMs do not all pull the
   // same weight tile out of L2 at the same moment (the accumulation order is free).
-  const int rot_tap = blockIdx.x % 9, rot_chunk = (blockIdx.x / 9) % n_src;
+  const int rot_id = CG2 ? blockIdx.x / 2 : blockIdx.x;
+  const int rot_tap = rot_id % 9, rot_chunk = (rot_id / 9) % n_src;
 
   if (tid == 0) {
     for (int i = 0; i < TC_NA; ++i) {
-      mbar_init(bar_a_full(i), TC_PROD);
+      mbar_init(bar_a_full(i), CG2 ? 2 * TC_PROD : TC_PROD);   // CG2: the producers of both CTAs arrive at the leader
       mbar_init(bar_a_empty(i), 1);
     }
     for (int i = 0; i < C::NB; ++i) {
       mbar_init(bar_b_full(i), 1);
       mbar_init(bar_b_empty(i), 1);
+      mbar_init(bar_b_peer(i), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full(i), 1);
-      mbar_init(bar_acc_empty(i), 128);
+      mbar_init(bar_acc_empty(i), CG2 ? 512 : 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(s0 + C::OFF_TMEM), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == TC_W_MMA) {
+    if (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(s0 + C::OFF_TMEM), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(s0 + C::OFF_TMEM), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
-  if (EPI == EPI_DELTA && warp < 4) {
+  if (EPI == EPI_DELTA && warp < 8) {
     float* ex = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
-    for (int i = tid; i < 9 * 256; i += 128) ex[i] = __ldg(a.w2 + i);
-    for (int i = tid; i < 256; i += 128) ex[9 * 256 + i] = __ldg(a.bias + i);
+    for (int i = tid; i < 9 * 256; i += 256) ex[i] = __ldg(a.w2 + i);
+    for (int i = tid; i < 256; i += 256) ex[9 * 256 + i] = __ldg(a.bias + i);
   }
   tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();       // barriers of both CTAs are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // arrive on a barrier that lives in the leader CTA
+  auto arrive_leader = [&](uint32_t bar) {
+    if (!CG2 || rank == 0) mbar_arrive(bar);
+    else mbar_arrive_cluster(bar, 0);
+  };
 
-  if (warp >= 6) {
-    // ================= A producers (64 threads) =================
-    const int pt = tid - 6 * 32;
+  if (warp >= TC_W_APROD) {
+    // ================= A producers =================
+    const int pt = tid - TC_W_APROD * 32;
+    const int p_hx = pt >> 3, p_g = pt & 7;          // this thread's halo column and k-group (pt < 80)
     int seq = 0;           // chunk sequence number over all tiles of this CTA
     int pending = -1;      // stage whose loads were issued but not yet published
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int tile = it * gridDim.x + blockIdx.x;
       const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
       for (int ci = 0; ci < n_src; ++ci, ++seq) {
         const int c = (ci + rot_chunk) % n_src;
@@ -151,12 +178,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           // disparity-neighbourhood encoder: channel k = 100 * (disp(y+k/7-3, x+k%7-3) - disp(y, x)), zero padded.
           // Stage the 24 x 16 disparity tile once, then one thread per halo pixel writes its 8 k-groups.
           float* sD = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
-          asm volatile("bar.sync 1, 64;" ::: "memory");           // previous tile's readers are done
+          asm volatile("bar.sync 1, 96;" ::: "memory");           // previous tile's readers are done
           for (int i = pt; i < TC_DT_H * TC_DT_W; i += TC_PROD) {
             const int yy = y0 - 4 + i / TC_DT_W, xx = x0 - 4 + i % TC_DT_W;
             sD[i] = (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) ? __ldg(a.disp + (long long)yy * a.w + xx) : 0.f;
           }
-          asm volatile("bar.sync 1, 64;" ::: "memory");
+          asm volatile("bar.sync 1, 96;" ::: "memory");
           for (int hp = pt; hp < TC_HPX; hp += TC_PROD) {
             const int hy = hp / TC_HW, hx = hp % TC_HW;
             const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
@@ -176,21 +203,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
               *reinterpret_cast<uint4*>(smem + (dst0 - s0) + g * TC_A_LBO + hp * 16) = *reinterpret_cast<const uint4*>(v);
             }
           }
-        } else {
-          const __half* src = a.src[c];
-          for (int i = pt; i < TC_HPX * 8; i += TC_PROD) {
-            const int hp = i >> 3, g = i & 7;
-            const int yy = y0 - 1 + hp / TC_HW, xx = x0 - 1 + hp % TC_HW;
-            const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
-            const __half* gp = src + ((long long)(ok ? yy : 0) * a.w + (ok ? xx : 0)) * 64 + g * 8;
-            cp_async16_zfill(dst0 + g * TC_A_LBO + hp * 16, gp, ok);
+        } else if (p_hx < TC_HW) {
+          // one halo column x one k-group per thread, walking down the 18 halo rows: 2 adds per copy
+          const int xx = x0 - 1 + p_hx;
+          const bool xok = xx >= 0 && xx < a.w;
+          const __half* gp = a.src[c] + ((long long)(y0 - 1) * a.w + (xok ? xx : 0)) * 64 + p_g * 8;
+          uint32_t dst = dst0 + p_g * TC_A_LBO + p_hx * 16;
+#pragma unroll 6
+          for (int hy = 0; hy < TC_HH; ++hy) {
+            const int yy = y0 - 1 + hy;
+            const bool ok = xok && yy >= 0 && yy < a.h;
+            cp_async16_zfill(dst, ok ? gp : a.src[c], ok);
+            gp += (long long)a.w * 64;
+            dst += TC_A_SBO;
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (pending >= 0) {   // publish the previous chunk while this one is in flight
           asm volatile("cp.async.wait_group 1;" ::: "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(bar_a_full(pending));
+          arrive_leader(bar_a_full(pending));
         }
         pending = st;
       }
@@ -198,12 +230,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
     if (pending >= 0) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_a_full(pending));
+      arrive_leader(bar_a_full(pending));
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_W_BPROD) {
     // ================= B producer =================
     if (lane == 0) {
-      const char* wsrc = reinterpret_cast<const char*>(a.wtc);
+      const char* wsrc = reinterpret_cast<const char*>(CG2 ? a.wtc2 : a.wtc);
       if (C::RESIDENT) {
         for (int s = 0; s < 9; ++s) {
           mbar_expect_tx(bar_b_full(s), C::B_BYTES);
@@ -212,25 +244,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
       } else {
         int seq = 0;
         const int n_steps = n_src * 9;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int it = 0; it < n_iter; ++it) {
           for (int si = 0; si < n_steps; ++si, ++seq) {
             const int s = ((si / 9 + rot_chunk) % n_src) * 9 + (si % 9 + rot_tap) % 9;
             const int st = seq % C::NB;
             mbar_wait(bar_b_empty(st), ((seq / C::NB) & 1) ^ 1);
             mbar_expect_tx(bar_b_full(st), C::B_BYTES);
-            bulk_g2s(sB + st * C::B_BYTES, wsrc + (size_t)s * C::B_BYTES, C::B_BYTES, bar_b_full(st));
+            // CG2: this CTA's half of the output channels is one contiguous slice of the pair layout
+            bulk_g2s(sB + st * C::B_BYTES, wsrc + ((size_t)s * (CG2 ? 2 : 1) + rank) * C::B_BYTES, C::B_BYTES,
+                     bar_b_full(st));
           }
         }
       }
     }
-  } else if (warp == 4) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(128, N);
-      int aseq = 0, bseq = 0, t = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+  } else if (warp == TC_W_MMA) {
+    // ================= MMA issuer (CG2: leader CTA only; the peer's warp relays its weight barriers) =================
+    if (lane == 0 && (!CG2 || rank == 0)) {
+      constexpr uint32_t idesc = umma_idesc(CG2 ? 256 : 128, N);
+      int aseq = 0, bseq = 0;
+      for (int t = 0; t < n_iter; ++t) {
         const int as = t & 1;
-        mbar_wait(bar_acc_empty(as), ((t >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        mbar_wait(bar_acc_empty(as), ((t >> 1) & 1) ^ 1);     // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * N;
         for (int c = 0; c < n_src; ++c, ++aseq) {
@@ -245,6 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
             } else {
               bst = bseq % C::NB;
               mbar_wait(bar_b_full(bst), (bseq / C::NB) & 1);
+              if (CG2) mbar_wait(bar_b_peer(bst), (bseq / C::NB) & 1);   // the peer's half has landed too
             }
             tc_fence_after();
             const int ky = tap / 3, kx = tap % 3;
@@ -253,27 +288,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
               const uint64_t ad = umma_desc(a0 + 2 * k16 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-              const uint64_t bd = umma_desc(b0 + 2 * k16 * (N * 16), N * 16, 128);
-              tc_mma_f16(d_tmem, ad, bd, idesc, (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u);
+              const uint64_t bd = umma_desc(b0 + 2 * k16 * (C::NLOC * 16), C::NLOC * 16, 128);
+              const uint32_t accum = (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u;
+              if (CG2) tc_mma2_f16(d_tmem, ad, bd, idesc, accum);
+              else tc_mma_f16(d_tmem, ad, bd, idesc, accum);
             }
-            if (!C::RESIDENT) tc_commit(bar_b_empty(bst));   // stage free once these MMAs have read it
+            if (!C::RESIDENT) {            // stage free (in both CTAs) once these MMAs have read it
+              if (CG2) tc_commit2_mc(bar_b_empty(bst));
+              else tc_commit(bar_b_empty(bst));
+            }
           }
-          tc_commit(bar_a_empty(ast));
+          if (CG2) tc_commit2_mc(bar_a_empty(ast));
+          else tc_commit(bar_a_empty(ast));
         }
-        tc_commit(bar_acc_full(as));                          // accumulator complete
+        if (CG2) tc_commit2_mc(bar_acc_full(as));             // accumulators complete (each CTA drains its own TMEM)
+        else tc_commit(bar_acc_full(as));
+      }
+    } else if (CG2 && rank == 1 && lane < C::NB) {
+      // peer CTA: forward "my half of weight stage `lane` has landed" to the leader; one lane per ring stage so that
+      // NB remote arrives are in flight (a remote arrive costs far more than one MMA step)
+      const int total_steps = n_iter * n_src * 9;
+      for (int bseq = lane; bseq < total_steps; bseq += C::NB) {
+        mbar_wait(bar_b_full(lane), (bseq / C::NB) & 1);
+        mbar_arrive_cluster(bar_b_peer(lane), 0);
       }
     }
   } else {
-    // ================= epilogue: thread = one pixel, all N channels =================
-    const int m = warp * 32 + lane;                 // row of the M tile = TMEM lane
+    // ================= epilogue: thread = one pixel, half of the N channels =================
+    // warps w and w+4 share TMEM lane quadrant w (a warp may only touch lanes 32*(warp%4)..+31) and split the columns
+    const int quad = warp & 3, chalf = warp >> 2;
+    const int m = quad * 32 + lane;                 // row of the M tile = TMEM lane
     const int r = m >> 3, cc = m & 7;
-    int t = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (int t = 0; t < n_iter; ++t) {
+      const int tile = t * gridDim.x + blockIdx.x;
       const int as = t & 1;
       const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
       mbar_wait(bar_acc_full(as), (t >> 1) & 1);
       tc_fence_after();
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * N;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * N;
       const int yy = y0 + r, xx = x0 + cc;
       const bool ok = yy < a.h && xx < a.w;
       const long long p = ok ? (long long)yy * a.w + xx : 0;
@@ -283,7 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
         for (int q = 0; q < 9; ++q) t9[q] = 0.f;
       }
 #pragma unroll 1
-      for (int cb = 0; cb < N / 32; ++cb) {
+      for (int cb = chalf * (N / 64); cb < (chalf + 1) * (N / 64); ++cb) {
         uint32_t raw[32];
         tc_ld32(lane_addr + cb * 32, raw);          // warp-collective: executed by every lane
         float v[32];
@@ -346,27 +398,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_acc_empty(as));               // accumulator stage may be overwritten
-      if (EPI == EPI_DELTA && ok) {
+      arrive_leader(bar_acc_empty(as));             // accumulator stage may be overwritten
+      if (EPI == EPI_DELTA && ok) {   // two partial sums per pixel (one per column half), added by the consumer
 #pragma unroll
-        for (int q = 0; q < 9; ++q) a.s9[p * 9 + q] = t9[q];
+        for (int q = 0; q < 9; ++q) a.s9[(p * 2 + chalf) * 9 + q] = t9[q];
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+  if (CG2) cluster_sync_all();     // no CTA leaves while its partner can still arrive on / read from its shared memory
+  if (warp == TC_W_MMA) {
+    if (CG2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)C::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
 
 // ---- host ----------------------------------------------------------------------------------------
+// N = 192 / 256 run as CTA pairs (cta_group::2); the N = 64 convs keep their weights resident and stay 1-CTA.
+template <int N>
+constexpr bool use_cg2() { return N != 64; }
+
+static int g_cg2_enabled = 0;   // CTA pairs are opt-in (cer_set_conv_variant(1) / CER_CONV=tc2): the relayed
+                                // weight barriers currently cost more than the halved operand traffic saves
+
 template <int N, int EPI>
 static int tc_configure_one() {
-  CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                TcCfg<N>::TOTAL));
+  CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TcCfg<N, false>::TOTAL));
+  if (use_cg2<N>())
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, use_cg2<N>()>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<N, use_cg2<N>()>::TOTAL));
   return CER_OK;
 }
 
@@ -379,12 +446,40 @@ int tc_configure() {
   return CER_OK;
 }
 
+void tc_set_cg2(int enabled) { g_cg2_enabled = enabled; }
+
 template <int N, int EPI>
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = ((a.w + TC_TW - 1) / TC_TW) * ((a.h + TC_TH - 1) / TC_TH);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
-  CER_LAUNCH(kind, (conv3x3_tc_kernel<N, EPI>), grid, TC_THREADS, TcCfg<N>::TOTAL, stream, a);
+  if (use_cg2<N>() && g_cg2_enabled && tiles >= 2) {
+    int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    grid &= ~1;                                             // whole CTA pairs
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<N, use_cg2<N>()>::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cer::g_timer) cer::timer_begin(kind, stream);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<N, EPI, use_cg2<N>()>, a);
+    if (cer::g_timer) cer::timer_end(stream);
+    ++cer::g_launches;
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("conv3x3_tc (cta pair) launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    return check_launch("conv3x3_tc");
+  }
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
+  CER_LAUNCH(kind, (conv3x3_tc_kernel<N, EPI, false>), grid, TC_THREADS, (TcCfg<N, false>::TOTAL), stream, a);
   return check_launch("conv3x3_tc");
 }
 

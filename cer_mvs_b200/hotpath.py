@@ -136,6 +136,35 @@ class DepthHotPath:
                 1.0 if scale is None else float(scale), o.ctypes.data, _lib.stream_ptr()), "cer_plan_run_host")
         return out
 
+    def submit_host(self, fmaps, net, inp, poses, intrinsics, scale=1.0, out=None):
+        """Pipelined run_host: enqueue one depth map (pinned host buffers) and return; its H2D copy overlaps the kernels
+        of the previous job.  Call wait_host() to wait for the oldest job; `out` (pinned) is valid after that."""
+        def as_np(x):
+            return x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        fm, nt, ip = as_np(fmaps), as_np(net), as_np(inp)
+        n_views = fm.shape[1] - 1
+        P = np.array(as_np(poses), dtype=np.float32).reshape(-1, 4, 4)
+        if scale is not None:
+            P[:, :3, 3] *= np.float32(scale)
+        K = np.array(as_np(intrinsics), dtype=np.float32).reshape(-1, 3, 3)
+        K[:, :2] /= 4
+        if out is None:
+            out = torch.empty(1, 1, self.h1, self.w1).pin_memory()
+        o = as_np(out)
+        for a in (fm, nt, ip):
+            if a.dtype not in (np.float16, np.float32) or not a.flags["C_CONTIGUOUS"]:
+                raise RuntimeError("submit_host: contiguous float16/float32 arrays expected")
+        self._keep = getattr(self, "_keep", [])[-3:] + [(fm, nt, ip, P, K, o)]     # keep host buffers alive while in flight
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cer_plan_submit_host(
+                self._plan, fm.ctypes.data, int(fm.dtype == np.float16), nt.ctypes.data, ip.ctypes.data,
+                int(nt.dtype == np.float16), P.ctypes.data, K.ctypes.data, n_views,
+                1.0 if scale is None else float(scale), o.ctypes.data, _lib.stream_ptr()), "cer_plan_submit_host")
+        return out
+
+    def wait_host(self):
+        _lib.check(_lib.lib().cer_plan_wait_host(self._plan), "cer_plan_wait_host")
+
     def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None):
         """One depth map over all ranks of ``group``: rank g builds views [g*V/G, (g+1)*V/G), one
         all-reduce(sum) of the partial mean volume per stage, replicated GRU loop."""

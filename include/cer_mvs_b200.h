@@ -122,8 +122,9 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     const float* corr, int slots, float* delta, int apply_delta, int stage, int h, int w,
                     cer_stream_t stream);
 
-/* Which tensor-core path the 3x3 convolutions use: 1 = tcgen05.mma + TMEM (default), 0 = mma.sync (the v1
- * kernels, kept for A/B validation; also selectable with CER_CONV=hmma).  Takes effect for launches and
+/* Which tensor-core path the 3x3 convolutions use: 2 = tcgen05.mma + TMEM, one CTA per SM (default);
+ * 1 = the same with CTA pairs (cta_group::2, M = 256) for the N >= 192 convolutions (CER_CONV=tc2, experimental);
+ * 0 = mma.sync (the v1 kernels, kept for A/B validation; CER_CONV=hmma).  Takes effect for launches and
  * graph captures issued afterwards. */
 int cer_set_conv_variant(int variant);
 
@@ -169,6 +170,16 @@ int cer_plan_run_device(cer_plan* plan, const void* fmaps, int fmaps_f16, const 
 int cer_plan_run_host(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
                       int ctx_f16, const float* poses, const float* intrinsics, int n_views,
                       float out_scale, float* disp_out, cer_stream_t stream);
+
+/* Pipelined form of cer_plan_run_host for throughput: submit returns as soon as the work is enqueued (the host->device
+ * copy of this job runs on a private copy stream and overlaps the kernels of the previous job; the disparity is copied
+ * back on the same copy stream).  At most two jobs are in flight (submit waits for the oldest one otherwise).  Host
+ * buffers should be pinned and must stay valid until the matching cer_plan_wait_host() returns; jobs complete in
+ * submission order. */
+int cer_plan_submit_host(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
+                         int ctx_f16, const float* poses, const float* intrinsics, int n_views, float out_scale,
+                         float* disp_out_host, cer_stream_t stream);
+int cer_plan_wait_host(cer_plan* plan);
 
 /* Stage-wise API for view-sharded multi-GPU runs: prepare -> for each stage
  * { build_stage (local views, scaled 1/total_views) ; [caller all-reduces partial_volume] ;

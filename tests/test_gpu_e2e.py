@@ -12,13 +12,13 @@ from util import H, V, W, h1, rel_l1, t, w1
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tcgen05", "hmma"], autouse=True)
+@pytest.fixture(params=["tcgen05", "tcgen05_cta_pair", "hmma"], autouse=True)
 def conv_variant(request):
     """Every test runs on both tensor-core paths: tcgen05.mma + TMEM (default) and mma.sync (v1)."""
     from cer_mvs_b200 import _lib
-    _lib.check(_lib.lib().cer_set_conv_variant(1 if request.param == "tcgen05" else 0))
+    _lib.check(_lib.lib().cer_set_conv_variant({"tcgen05": 2, "tcgen05_cta_pair": 1, "hmma": 0}[request.param]))
     yield request.param
-    _lib.lib().cer_set_conv_variant(1)
+    _lib.lib().cer_set_conv_variant(2)
 TOL = 1e-3          # BASELINE.json north_star: "within 1e-3 relative L1 on disparity"
 
 
@@ -101,6 +101,25 @@ def test_graph_and_eager_identical_and_host_path(golden):
                        sc["poses"], sc["intrinsics"], scale=1.0)
     assert np.array_equal(a, host)
     assert hp.last_launch_count > 0
+
+
+def test_pipelined_host_path_matches(golden):
+    """cer_plan_submit_host / wait_host (copies overlapped with the previous job) == run_host, job by job."""
+    g = golden("e2e_fp32_drift")
+    sc, sd, cascade = _inputs(g)
+    hp, ref = _hot(sc, sd, cascade, g, torch.float16)
+    fm = t(sc["fmaps"]).half().pin_memory()
+    nets = [(t(g["net"]) * s).half().pin_memory() for s in (1.0, 0.5, 0.25, 1.0)]
+    inp = t(g["inp"]).half().pin_memory()
+    want = [hp.run_host(fm, n, inp, sc["poses"], sc["intrinsics"], 1.0).copy() for n in nets]
+    outs = [torch.empty(1, 1, h1, w1).pin_memory() for _ in nets]
+    for n, o in zip(nets, outs):
+        hp.submit_host(fm, n, inp, sc["poses"], sc["intrinsics"], 1.0, out=o)
+    for _ in nets:
+        hp.wait_host()
+    for o, w in zip(outs, want):
+        assert np.array_equal(o.numpy(), w)
+    assert np.array_equal(want[0], ref) and not np.array_equal(want[1], ref)
 
 
 def test_dropin_classes_in_reference_loop(golden):
