@@ -141,18 +141,20 @@ __global__ void __launch_bounds__(256) corr_enc1_kernel(const float* __restrict_
 // touch HBM.  Block = 128 pixels; the level-0 volume rows are staged in shared memory (coalesced), every
 // thread pair produces the 33 taps of one pixel as the fp16 A row of the 1x1-conv MMA.
 // ------------------------------------------------------------------------------------------
+constexpr int kLE_PIX = 64;     // pixels per block (4 threads per pixel for the lookup, 4 MMA warps)
+
 __global__ void __launch_bounds__(256) lookup_enc1_kernel(
     const float* __restrict__ volume, const float* __restrict__ origin, float* __restrict__ disp,
     const float* __restrict__ s9, int parts, const float* __restrict__ bd1, int apply_prev, int D, float incre,
     const __half* __restrict__ w1, const float* __restrict__ b1, __half* __restrict__ e1, int h, int w) {
   extern __shared__ __align__(16) unsigned char fsm[];
-  __half* sA = reinterpret_cast<__half*>(fsm);                          // [128][kA1Pitch]
-  __half* sW = sA + 128 * kA1Pitch;                                     // [48][kW1Pitch]
-  float* sC = reinterpret_cast<float*>(sW + kCorrK * kW1Pitch);         // [128] lookup coordinate
-  float* rows = sC + 128;                                               // [128][D + 1]
+  __half* sA = reinterpret_cast<__half*>(fsm);                          // [kLE_PIX][kA1Pitch]
+  __half* sW = sA + kLE_PIX * kA1Pitch;                                 // [48][kW1Pitch]
+  float* sC = reinterpret_cast<float*>(sW + kCorrK * kW1Pitch);         // [kLE_PIX] lookup coordinate
+  float* rows = sC + kLE_PIX;                                           // [kLE_PIX][D + 1]
   const long long px = (long long)h * w;
-  const long long p0 = (long long)blockIdx.x * 128;
-  const int npix = (int)min((long long)128, px - p0);
+  const long long p0 = (long long)blockIdx.x * kLE_PIX;
+  const int npix = (int)min((long long)kLE_PIX, px - p0);
   const int tid = threadIdx.x;
   const int pitch = D + 1;
   // stage volume rows
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) lookup_enc1_kernel(
     *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
   }
   // disparity of this block's pixels (after applying the pending delta) -> lookup coordinate
-  if (tid < 128) {
+  if (tid < kLE_PIX) {
     float c = 0.f;
     if (tid < npix) {
       const long long p = p0 + tid;
@@ -197,24 +199,22 @@ __global__ void __launch_bounds__(256) lookup_enc1_kernel(
     sC[tid] = c;
   }
   __syncthreads();
-  {  // lookup: thread pair per pixel, 24 of the 48 A columns each (33 real taps, the rest zero); the tap loop is
+  {  // lookup: 4 threads per pixel, 12 of the 48 A columns each (33 real taps, the rest zero); the tap loops are
      // fully unrolled so level and offset are compile-time and the independent taps overlap
-    const int pl = tid & 127, half = tid >> 7;
+    const int pl = tid & (kLE_PIX - 1), quarter = tid / kLE_PIX;
     const float* row = rows + pl * pitch;
     const float c = sC[pl];
     const bool live = pl < npix;
     __half* arow = sA + pl * kA1Pitch;
-    if (half == 0) {
-#pragma unroll
-      for (int k = 0; k < 24; ++k) arow[k] = __float2half_rn(live ? lookup_tap(row, D, k / 11, k % 11 - 5, c) : 0.f);
-    } else {
-#pragma unroll
-      for (int k = 24; k < 48; ++k)
-        arow[k] = __float2half_rn((live && k < kCorrPlanes) ? lookup_tap(row, D, k / 11, k % 11 - 5, c) : 0.f);
-    }
+#define CER_TAPS(K0)                                                                                        \
+  _Pragma("unroll") for (int k = (K0); k < (K0) + 12; ++k)                                                  \
+      arow[k] = __float2half_rn((live && k < kCorrPlanes) ? lookup_tap(row, D, k / 11, k % 11 - 5, c) : 0.f);
+    if (quarter == 0) { CER_TAPS(0) } else if (quarter == 1) { CER_TAPS(12) } else if (quarter == 2) { CER_TAPS(24) } else { CER_TAPS(36) }
+#undef CER_TAPS
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
+  if (warp >= kLE_PIX / 16) return;          // 4 MMA warps x 16 pixels
   float acc[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) lookup_enc1_kernel(
 }
 
 static size_t lookup_enc1_smem(int D) {
-  return (size_t)128 * kA1Pitch * 2 + (size_t)kCorrK * kW1Pitch * 2 + 128 * 4 + (size_t)128 * (D + 1) * 4;
+  return (size_t)kLE_PIX * kA1Pitch * 2 + (size_t)kCorrK * kW1Pitch * 2 + kLE_PIX * 4 + (size_t)kLE_PIX * (D + 1) * 4;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -586,7 +586,7 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
     return CER_ERR_INVALID;
   }
   const bool tc = conv_variant() == 1;
-  CER_LAUNCH(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, 128), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
+  CER_LAUNCH(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
              ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre, (const __half*)(B + L.w1),
              (const float*)(B + L.b1), ws.e1, h, w);
   if (!tc) CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);

@@ -283,12 +283,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
             }
             tc_fence_after();
             const int ky = tap / 3, kx = tap % 3;
-            const uint32_t a0 = sA + ast * TC_A_BYTES + (ky * TC_HW + kx) * 16;
-            const uint32_t b0 = sB + bst * C::B_BYTES;
+            // descriptors of the 4 K=16 slices differ only in the start-address field: one 64-bit add each
+            const uint64_t ad0 = umma_desc(sA + ast * TC_A_BYTES + (ky * TC_HW + kx) * 16, TC_A_LBO, TC_A_SBO);
+            const uint64_t bd0 = umma_desc(sB + bst * C::B_BYTES, C::NLOC * 16, 128);
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) {
-              const uint64_t ad = umma_desc(a0 + 2 * k16 * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-              const uint64_t bd = umma_desc(b0 + 2 * k16 * (C::NLOC * 16), C::NLOC * 16, 128);
+              const uint64_t ad = ad0 + (uint64_t)((2 * k16 * TC_A_LBO) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)((2 * k16 * (C::NLOC * 16)) >> 4);
               const uint32_t accum = (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u;
               if (CG2) tc_mma2_f16(d_tmem, ad, bd, idesc, accum);
               else tc_mma_f16(d_tmem, ad, bd, idesc, accum);
@@ -342,13 +343,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]);
         const int n0 = cb * 32;
+        if (EPI == EPI_RELU || EPI == EPI_GATES) {      // bias: 8 uniform 16-byte loads
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0) + q4);
+            v[4 * q4] += bb.x; v[4 * q4 + 1] += bb.y; v[4 * q4 + 2] += bb.z; v[4 * q4 + 3] += bb.w;
+          }
+        }
         if (EPI == EPI_RELU) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaxf(h_round(v[e] + __ldg(a.bias + n0 + e)), 0.f);
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(h_round(v[e]), 0.f);
           if (ok) st_half32(a.out_h + p * 64 + n0, v);
         } else if (EPI == EPI_GATES) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += __ldg(a.bias + n0 + e);
           if (n0 < 64) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fast_sigmoid(h_round(v[e]));
