@@ -122,6 +122,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -133,16 +140,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        # the sampler runs from before the warm-up; keep the samples that arrived inside the timed region
+        rows = [r for (ts, r) in self.rows if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts) + 0.05)]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-3:]]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -215,17 +226,19 @@ def run_ours(args):
         return float(tt.item())
 
     # ---- device-resident throughput (value) ----
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
+    clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
     e1.record()
     barrier()
+    clocks.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop()
     launches = hp.last_launch_count * args.steps
@@ -337,7 +350,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-rows", type=int, default=24, help="rows of the 296-row grid in one CPU sample")

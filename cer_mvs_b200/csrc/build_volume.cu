@@ -39,10 +39,20 @@ __device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
   return r;
 }
 
+// base + 32-bit byte offset as ONE instruction (IMAD.WIDE.U32) instead of a 64-bit add pair
+__device__ __forceinline__ const void* ptr_add_u32(const void* base, uint32_t byte_off) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(byte_off), "l"(reinterpret_cast<uint64_t>(base)));
+  return reinterpret_cast<const void*>(r);
+}
+
 template <>
 struct FeatSlice<__half> {
   uint4 v;
   __device__ __forceinline__ void load(const __half* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void load_off(const __half* base, uint32_t byte_off) {
+    v = __ldg(reinterpret_cast<const uint4*>(ptr_add_u32(base, byte_off)));
+  }
   __device__ __forceinline__ float dot(const FeatSlice& o) const {
     float d = fhfma_lo(v.x, o.v.x, 0.f);
     d = fhfma_hi(v.x, o.v.x, d);
@@ -62,6 +72,9 @@ struct FeatSlice<float> {
   __device__ __forceinline__ void load(const float* p) {
     a = __ldg(reinterpret_cast<const float4*>(p));
     b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void load_off(const float* base, uint32_t byte_off) {
+    load(reinterpret_cast<const float*>(ptr_add_u32(base, byte_off)));
   }
   __device__ __forceinline__ float dot(const FeatSlice& o) const {
     float d = a.x * o.a.x;
@@ -84,6 +97,7 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
     int h, int w) {
   __shared__ float sP[kMaxPairs][12];
   __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
+  __shared__ __align__(16) int sS[32 * 8 * 8];   // per 8-lane group: 8 samples x {4 offsets, 4 weights}
   for (int t = threadIdx.x; t < n_pairs * 12; t += blockDim.x) sP[t / 12][t % 12] = Pij[(t / 12) * 16 + (t % 12)];
   for (int t = threadIdx.x; t < n_pairs; t += blockDim.x) {
     sI[t] = ii[t];
@@ -132,35 +146,49 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
       u = u < -1e4f ? -1e4f : (u > 1e4f ? 1e4f : u);  // NaN-preserving clamp
       v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
       const float fu = floorf(u), fv = floorf(v);
-      const float my_dx = u - fu, my_dy = v - fv;
+      const float dx = u - fu, dy = v - fv;
       const int ix = (int)fu, iy = (int)fv;
-      // the owner lane resolves the four corners once: element offset of the pixel row, or -1 outside fmap2
-      int my_o[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int yy = iy + (c >> 1), xx = ix + (c & 1);
-        my_o[c] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? (yy * w + xx) * kFeatC : -1;
+      // The owner lane resolves the sample once and publishes it through shared memory (two 16-byte broadcast
+      // reads per lane instead of shuffles + per-lane bounds logic):
+      //   * element offsets of the four corner pixels, clamped into fmap2 so every load is legal and unpredicated;
+      //   * row / column weights with out-of-range rows / columns zeroed: (dot * wy) * wx is then exactly 0 for a
+      //     corner outside fmap2, which is what the reference adds for it (zero features, kernel.cu:81-84).
+      //     NaN coordinates keep NaN weights, so the output is NaN like the reference's.
+      {
+        const int y0c = min(max(iy, 0), h - 1), y1c = min(max(iy + 1, 0), h - 1);
+        const int x0c = min(max(ix, 0), w - 1), x1c = min(max(ix + 1, 0), w - 1);
+        const float wy0 = (iy >= 0 && iy < h) ? 1.f - dy : ((dy != dy) ? dy : 0.f);
+        const float wy1 = (iy + 1 >= 0 && iy + 1 < h) ? dy : ((dy != dy) ? dy : 0.f);
+        const float wx0 = (ix >= 0 && ix < w) ? 1.f - dx : ((dx != dx) ? dx : 0.f);
+        const float wx1 = (ix + 1 >= 0 && ix + 1 < w) ? dx : ((dx != dx) ? dx : 0.f);
+        constexpr int kPixBytes = kFeatC * (int)sizeof(T);     // byte offsets (an image is < 4 GB)
+        int4 o4 = make_int4((y0c * w + x0c) * kPixBytes, (y0c * w + x1c) * kPixBytes, (y1c * w + x0c) * kPixBytes,
+                            (y1c * w + x1c) * kPixBytes);
+        int4* slot = reinterpret_cast<int4*>(sS + (threadIdx.x >> 3) * 8 * 8 + lane * 8);
+        slot[0] = o4;
+        reinterpret_cast<float4*>(slot)[1] = make_float4(wy0, wy1, wx0, wx1);
       }
+      __syncwarp();
 
       float part[8];
+      const int* grp = sS + (threadIdx.x >> 3) * 8 * 8;
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const int o0 = __shfl_sync(0xffffffffu, my_o[0], s, 8);
-        const int o1 = __shfl_sync(0xffffffffu, my_o[1], s, 8);
-        const int o2 = __shfl_sync(0xffffffffu, my_o[2], s, 8);
-        const int o3 = __shfl_sync(0xffffffffu, my_o[3], s, 8);
-        const float dx = __shfl_sync(0xffffffffu, my_dx, s, 8);
-        const float dy = __shfl_sync(0xffffffffu, my_dy, s, 8);
+        const int4 o4 = *reinterpret_cast<const int4*>(grp + s * 8);
+        const float4 wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
         FeatSlice<T> f2;
-        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-        if (o0 >= 0) { f2.load(img2 + o0); d00 = f1.dot(f2); }
-        if (o1 >= 0) { f2.load(img2 + o1); d01 = f1.dot(f2); }
-        if (o2 >= 0) { f2.load(img2 + o2); d10 = f1.dot(f2); }
-        if (o3 >= 0) { f2.load(img2 + o3); d11 = f1.dot(f2); }
-        // (dot * wy) * wx per corner (correlation_kernel.cu:97-100); NaN coordinates give NaN like the reference
-        const float wy0 = 1.f - dy, wx0 = 1.f - dx;
-        part[s] = ((d00 * wy0) * wx0 + (d01 * wy0) * dx) + ((d10 * dy) * wx0 + (d11 * dy) * dx);
+        f2.load_off(img2, (uint32_t)o4.x);
+        const float d00 = f1.dot(f2);
+        f2.load_off(img2, (uint32_t)o4.y);
+        const float d01 = f1.dot(f2);
+        f2.load_off(img2, (uint32_t)o4.z);
+        const float d10 = f1.dot(f2);
+        f2.load_off(img2, (uint32_t)o4.w);
+        const float d11 = f1.dot(f2);
+        // (dot * wy) * wx per corner (correlation_kernel.cu:97-100)
+        part[s] = ((d00 * wt.x) * wt.z + (d01 * wt.x) * wt.w) + ((d10 * wt.y) * wt.z + (d11 * wt.y) * wt.w);
       }
+      __syncwarp();   // the slots are rewritten for the next view
       // butterfly: lane L ends with the group-wide total of sample L
       float k4[4], k2[2];
 #pragma unroll
