@@ -188,6 +188,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (cer_mvs_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     _lib.check(_lib.lib().cer_device_check(), "device check")
+    if args.conv_variant is not None:
+        _lib.check(_lib.lib().cer_set_conv_variant(args.conv_variant), "conv variant")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -356,6 +358,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=24, help="rows of the 296-row grid in one CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="ncu helper: warm-up + one eager step only")
+    ap.add_argument("--conv-variant", type=int, default=None, help="cer_set_conv_variant (A/B experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

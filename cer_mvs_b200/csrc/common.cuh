@@ -50,7 +50,33 @@ extern thread_local KernelTimer* g_timer; // non-null while a plan runs eagerly 
 void timer_begin(int kind, cudaStream_t s);
 void timer_end(cudaStream_t s);
 
+// Programmatic dependent launch (PDL): a kernel launched with CER_LAUNCH_PDL may start while its predecessor in
+// the stream is still draining; it must call pdl_wait() before touching anything the predecessor wrote (or
+// writing anything the predecessor reads).  Launch latency, barrier/TMEM set-up and constant-weight prefetch
+// then overlap the predecessor's tail.  g_pdl = 0 (CER_PDL=0) falls back to plain stream order.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace cer
+
+#define CER_LAUNCH_PDL(kind, kernel, grid, block, smem, stream, ...)                         \
+  do {                                                                                       \
+    if (cer::g_timer) cer::timer_begin((kind), (cudaStream_t)(stream));                      \
+    cudaLaunchConfig_t cfg_ = {};                                                            \
+    cfg_.gridDim = dim3(grid);                                                               \
+    cfg_.blockDim = dim3(block);                                                             \
+    cfg_.dynamicSmemBytes = (smem);                                                          \
+    cfg_.stream = (cudaStream_t)(stream);                                                    \
+    cudaLaunchAttribute attr_[1];                                                            \
+    attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                        \
+    attr_[0].val.programmaticStreamSerializationAllowed = 1;                                 \
+    cfg_.attrs = attr_;                                                                      \
+    cfg_.numAttrs = cer::g_pdl ? 1 : 0;                                                      \
+    cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                          \
+    if (cer::g_timer) cer::timer_end((cudaStream_t)(stream));                                \
+    ++cer::g_launches;                                                                       \
+  } while (0)
 
 #define CER_LAUNCH(kind, kernel, grid, block, smem, stream, ...)                \
   do {                                                                          \

@@ -1,6 +1,7 @@
 // Correlation-side small kernels: error plumbing, the alt_cuda_corr.forward drop-in, layout
 // changes, projection matrices, pyramid pooling and the fused pyramid lookup.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -10,6 +11,7 @@ namespace cer {
 
 static thread_local char g_err[512] = "";
 thread_local long long g_launches = 0;
+int g_pdl = []() { const char* e = getenv("CER_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 
 void set_error(const char* fmt, ...) {
   va_list ap;

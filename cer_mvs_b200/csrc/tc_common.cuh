@@ -74,6 +74,15 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One lane of a fully converged warp (the warp keeps executing uniformly, so descriptors and barrier addresses stay
+// in uniform registers: issuing from `if (lane == 0)` code costs ~190 cycles per tcgen05.mma in R2UR/waterfall
+// sequences, more than the 96-cycle MMA itself).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- 2-CTA (cta_group::2) helpers ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -93,6 +102,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
 __device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {   // both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// 1-CTA MMAs, commit delivered to the barrier at the same offset in every CTA of the mask
+__device__ __forceinline__ void tc_commit1_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in the mask; complete_tx on each CTA's barrier
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+// TMA tensor load issued by either CTA of a cta_group::2 pair; the transaction bytes are credited to the barrier at
+// the same offset in the EVEN CTA (the MMA leader) -- clearing the peer bit of the shared-window address selects it.
+__device__ __forceinline__ void tma2d_cg2(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
 }
 __device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {

@@ -28,6 +28,7 @@ struct ConvArgs {
   float* qx;           // EPI_GATES: write; EPI_GRUOUT: read
   const float* w2;     // EPI_DELTA: [9][256]
   float* s9;           // EPI_DELTA: [px][2][9] partial dots of the second delta conv
+  unsigned long long* prof;   // optional (tools/conv_roles.py): per-role wait/work cycle counters of CTA 0, else null
 };
 
 struct UpdateWs {

@@ -157,6 +157,12 @@ __global__ void __launch_bounds__(256) lookup_enc1_kernel(
   const int npix = (int)min((long long)kLE_PIX, px - p0);
   const int tid = threadIdx.x;
   const int pitch = D + 1;
+  pdl_trigger();
+  for (int i = tid; i < kCorrK * kHid / 8; i += 256) {   // 1x1 weights: constants, fetched before the dependency wait
+    const int k = i / (kHid / 8), c = i % (kHid / 8);
+    *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
+  }
+  pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
   // stage volume rows
   const float* vsrc = volume + p0 * D;
   if ((D & 3) == 0) {
@@ -169,10 +175,6 @@ __global__ void __launch_bounds__(256) lookup_enc1_kernel(
     }
   } else {
     for (int i = tid; i < npix * D; i += 256) rows[(i / D) * pitch + (i % D)] = __ldg(vsrc + i);
-  }
-  for (int i = tid; i < kCorrK * kHid / 8; i += 256) {
-    const int k = i / (kHid / 8), c = i % (kHid / 8);
-    *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
   }
   // disparity of this block's pixels (after applying the pending delta) -> lookup coordinate
   if (tid < kLE_PIX) {
@@ -466,6 +468,8 @@ __global__ void __launch_bounds__(256) disp_update_kernel(const float* __restric
                                                          float* __restrict__ delta, int apply, int h, int w) {
   const long long px = (long long)h * w;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (p >= px) return;
   const int x = (int)(p % w), y = (int)(p / w);
   float s = 0.f;
@@ -492,13 +496,14 @@ static int configure_conv() {
   return CER_OK;
 }
 
-void tc_set_cg2(int enabled);
+void tc_set_pair_mode(int mode);   // 0 single CTA, 1 cta_group::2 pairs, 2 multicast pairs
 static int g_variant = -1;
 int conv_variant() {
   if (g_variant < 0) {
     const char* e = getenv("CER_CONV");
     g_variant = (e && !strcmp(e, "hmma")) ? 0 : 1;
-    if (e && !strcmp(e, "tc2")) tc_set_cg2(1);
+    if (e && !strcmp(e, "tc2")) tc_set_pair_mode(1);
+    if (e && !strcmp(e, "tc1")) tc_set_pair_mode(0);
   }
   return g_variant;
 }
@@ -519,9 +524,15 @@ int update_configure() {
   return CER_OK;
 }
 
+static unsigned long long* g_conv_prof = nullptr;   // device buffer [4 kernels][32] set by cer_debug_set_conv_profile
+
 template <int N_TILE, int EPI>
 static int launch_conv(const ConvArgs& a_in, cudaStream_t stream) {
-  if (conv_variant() == 1) return launch_conv_tc_dispatch(N_TILE, EPI, a_in, stream);
+  if (conv_variant() == 1) {
+    ConvArgs a2 = a_in;
+    a2.prof = g_conv_prof ? g_conv_prof + EPI * 32 : nullptr;
+    return launch_conv_tc_dispatch(N_TILE, EPI, a2, stream);
+  }
   const ConvArgs& a = a_in;
   constexpr int smem = ConvSmem<N_TILE>::TOTAL;
   const int tiles = ((a.w + TW - 1) / TW) * ((a.h + TH - 1) / TH);
@@ -586,7 +597,7 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
     return CER_ERR_INVALID;
   }
   const bool tc = conv_variant() == 1;
-  CER_LAUNCH(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
+  CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
              ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre, (const __half*)(B + L.w1),
              (const float*)(B + L.b1), ws.e1, h, w);
   if (!tc) CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
@@ -618,7 +629,7 @@ int update_apply_delta(const void* blob, void* workspace, float* disp, int stage
   const char* B = (const char*)blob;
   const long long px = (long long)h * w;
   UpdateWs ws = carve_ws(workspace, px);
-  CER_LAUNCH(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, conv_variant() == 1 ? 2 : 1,
+  CER_LAUNCH_PDL(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, conv_variant() == 1 ? 2 : 1,
              (const float*)(B + L.bd1[stage]), disp, (float*)nullptr, 1, h, w);
   return check_launch("disp_update");
 }
@@ -725,11 +736,19 @@ int cer_pack_update_weights(const float* const* w, void* blob_host) {
   return CER_OK;
 }
 
+// Debug hook: device buffer of 4 x 32 uint64 receiving per-role wait/work cycle counters of CTA 0 of each tcgen05 conv
+// kernel (epilogue kind index: 0 corr-encoder, 1 gates, 2 q/GRU, 3 delta); pass NULL to switch it off.
+int cer_debug_set_conv_profile(void* dev_buf) {
+  g_conv_prof = (unsigned long long*)dev_buf;
+  return CER_OK;
+}
+
 int cer_set_conv_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 2,
-              "cer_set_conv_variant: 0 (mma.sync), 1 (tcgen05, CTA pairs for N >= 192) or 2 (tcgen05, single CTA, default)");
+  CER_REQUIRE(variant >= 0 && variant <= 4,
+              "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs, 2 tcgen05 one tile per CTA (default), "
+              "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA");
   g_variant = variant == 0 ? 0 : 1;
-  tc_set_cg2(variant == 1);
+  tc_set_pair_mode(variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : 0);
   return CER_OK;
 }
 

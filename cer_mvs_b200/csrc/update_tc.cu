@@ -17,6 +17,10 @@
 //              same tile (LBO = 180*16 B between k-groups, SBO = 10*16 B between image rows = 8-row
 //              core-matrix groups).  The disparity-encoder chunk of the gate conv (core/update.py:80-85,97)
 //              is computed here straight from disp instead of being read from HBM.
+#include <string.h>
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "tc_common.cuh"
 #include "update_common.cuh"
 
@@ -28,27 +32,46 @@ constexpr int TC_HPX = TC_HW * TC_HH;          // 180 halo pixels
 constexpr int TC_A_LBO = TC_HPX * 16;          // bytes between the two 8-channel groups of one K=16 slice
 constexpr int TC_A_SBO = TC_HW * 16;           // bytes between 8-row groups (= image rows of the M tile)
 constexpr int TC_A_BYTES = 8 * TC_A_LBO;       // one 64-channel chunk: 23 040 B
-constexpr int TC_NA = 3;                       // A ring depth (chunks)
 constexpr int TC_PROD = 96;                    // A producer threads (80 active: one per (halo column, k-group))
 constexpr int TC_W_MMA = 8, TC_W_BPROD = 9, TC_W_APROD = 10;   // warp roles; warps 0-7 are the epilogue
-constexpr int TC_THREADS = (TC_W_APROD + TC_PROD / 32) * 32;    // 416
+constexpr int TC_W_MMA2 = TC_W_APROD + TC_PROD / 32;            // second MMA issuer (13)
+constexpr int TC_THREADS = (TC_W_MMA2 + 1) * 32;                // 448
+// Two issuer warps taking alternate (chunk, tap) steps buy ~5 % on the gate conv but make the fp32 accumulation order
+// (and therefore the last bit of some outputs) depend on how the two warps interleave: off, results are bit-reproducible.
+constexpr bool kTwoIssuers = false;
 constexpr int TC_DT_H = TC_HH + 6, TC_DT_W = TC_HW + 6;   // disparity tile for the 7x7 encoder: 24 x 16
 
 // CG2: the CTA pair of a 2-CTA cluster runs one M=256 tcgen05.mma.cta_group::2 per step: each CTA supplies its own
 // 128 pixel rows of A and HALF of the weight tile (N/2 output channels), which halves the weight traffic from L2
 // and the shared-memory operand reads per SM -- the limiter of the 1-CTA form.
-template <int N, bool CG2 = false>
+// MC2: a 2-CTA cluster of ordinary 1-CTA MMAs in which each CTA fetches HALF of every weight tile and multicasts it
+// into both CTAs' shared memory (cp.async.bulk ... .multicast::cluster): the weight traffic out of L2 -- 885 KB per
+// 128-pixel tile for the gate conv, the measured limiter -- is halved with no cross-CTA software signalling at all
+// (stage release = tcgen05.commit multicast to both CTAs' barriers).
+// MT2: one CTA owns TWO M = 128 tiles and issues both MMAs against every weight stage, so the weight bytes an SM
+// has to pull through its ~65 GB/s L2 port per output pixel are halved (that port, not the tensor pipe, bounds the
+// streamed-weight convs); the accumulators then fill TMEM (2 x N columns), so the epilogue is not double-buffered.
+enum TcMode { TC_SINGLE = 0, TC_CG2 = 1, TC_MC2 = 2, TC_MT2 = 3 };
+
+template <int N, int MODE = TC_SINGLE>
 struct TcCfg {
+  static constexpr bool CG2 = MODE == TC_CG2;
+  static constexpr bool MC2 = MODE == TC_MC2;
+  static constexpr int MT = MODE == TC_MT2 ? 2 : 1;             // M tiles per CTA work unit
   static constexpr bool RESIDENT = (N == 64);                 // all 9 weight tiles stay in smem
-  static constexpr int NB = RESIDENT ? 9 : (CG2 ? 8 : ((N == 256) ? 4 : 6));   // weight ring depth
+  static constexpr int NB = RESIDENT ? 9 : (CG2 ? (N == 256 ? 8 : 12) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
   static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
+  // A ring depth (64-channel chunks).  Deeper rings / more accumulator stages for the N = 64 convs were measured
+  // slower (q/GRU 36 -> 44 us): those kernels are bound by their per-tile latency chain, not by ring capacity.
+  static constexpr int NA = MT == 2 ? 4 : 3;
+  static constexpr int NACC = MT == 2 ? 1 : 2;                    // TMEM accumulator stages (of MT x N columns)
   static constexpr int B_BYTES = 64 * NLOC * 2;
-  static constexpr int TMEM_COLS = (2 * N <= 128) ? 128 : (2 * N <= 256 ? 256 : 512);   // 2 accumulator stages
-  static constexpr int OFF_B = TC_NA * TC_A_BYTES;
+  static constexpr int TMEM_COLS = (NACC * MT * N <= 128) ? 128 : (NACC * MT * N <= 256 ? 256 : 512);
+  static constexpr int OFF_B = NA * TC_A_BYTES;
   static constexpr int OFF_EXTRA = OFF_B + NB * B_BYTES;                  // DELTA: w2 [9][256] f32 + bias [256] f32
   static constexpr int EXTRA_BYTES = (N == 256) ? (9 * 256 + 256) * 4 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
   static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
-  static constexpr int NUM_BAR = 2 * TC_NA + 3 * NB + 4;      // a_full/empty, b_full/empty/peer_full, acc_full/empty
+  static constexpr int NUM_BAR = 2 * NA + 3 * NB + 2 * NACC;  // a_full/empty, b_full/empty/peer_full, acc_full/empty
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
@@ -74,6 +97,21 @@ __device__ __forceinline__ void st_half32(__half* dst, const float (&v)[32]) {
     *reinterpret_cast<uint4*>(dst + 8 * q) = pk;
   }
 }
+__device__ __forceinline__ void ldg_half32_raw(const __half* src, uint4 (&pk)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pk[q] = *reinterpret_cast<const uint4*>(src + 8 * q);
+}
+__device__ __forceinline__ void unpack_half32(const uint4 (&pk)[4], float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&pk[q].x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&pk[q].y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&pk[q].z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&pk[q].w));
+    v[8 * q + 0] = a.x; v[8 * q + 1] = a.y; v[8 * q + 2] = b.x; v[8 * q + 3] = b.y;
+    v[8 * q + 4] = c.x; v[8 * q + 5] = c.y; v[8 * q + 6] = d.x; v[8 * q + 7] = d.y;
+  }
+}
 __device__ __forceinline__ void ld_half32(const __half* src, float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -88,47 +126,54 @@ __device__ __forceinline__ void ld_half32(const __half* src, float (&v)[32]) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int N, int EPI, bool CG2>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArgs a) {
-  using C = TcCfg<N, CG2>;
+template <int N, int EPI, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArgs a,
+                                                                  const __grid_constant__ CUtensorMap wmap) {
+  using C = TcCfg<N, MODE>;
+  constexpr bool CG2 = C::CG2, MC2 = C::MC2;
+  constexpr int MT = C::MT;
+  static_assert(MT == 1 || (!C::RESIDENT && N * 2 <= 512), "MT2 is for the streamed-weight convs");
+  static_assert(!(MC2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
   static_assert(!(CG2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sA = s0, sB = s0 + C::OFF_B, sBar = s0 + C::OFF_BAR;
   auto bar_a_full = [&](int i) { return sBar + 8 * i; };
-  auto bar_a_empty = [&](int i) { return sBar + 8 * (TC_NA + i); };
-  auto bar_b_full = [&](int i) { return sBar + 8 * (2 * TC_NA + i); };
-  auto bar_b_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + C::NB + i); };
-  auto bar_b_peer = [&](int i) { return sBar + 8 * (2 * TC_NA + 2 * C::NB + i); };      // CG2, leader only
-  auto bar_acc_full = [&](int i) { return sBar + 8 * (2 * TC_NA + 3 * C::NB + i); };
-  auto bar_acc_empty = [&](int i) { return sBar + 8 * (2 * TC_NA + 3 * C::NB + 2 + i); };
-  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+  auto bar_a_empty = [&](int i) { return sBar + 8 * (C::NA + i); };
+  auto bar_b_full = [&](int i) { return sBar + 8 * (2 * C::NA + i); };
+  auto bar_b_empty = [&](int i) { return sBar + 8 * (2 * C::NA + C::NB + i); };
+  auto bar_b_peer = [&](int i) { return sBar + 8 * (2 * C::NA + 2 * C::NB + i); };      // CG2, leader only
+  auto bar_acc_full = [&](int i) { return sBar + 8 * (2 * C::NA + 3 * C::NB + i); };
+  auto bar_acc_empty = [&](int i) { return sBar + 8 * (2 * C::NA + 3 * C::NB + C::NACC + i); };
+  const uint32_t rank = (CG2 || MC2) ? cluster_ctarank() : 0u;      // CG2: 0 = leader (issues the MMAs)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();      // let the next kernel of the chain get scheduled as SMs drain (it waits on pdl_wait itself)
   const int tiles_x = (a.w + TC_TW - 1) / TC_TW;
   const int n_tiles = tiles_x * ((a.h + TC_TH - 1) / TC_TH);
   // every CTA runs the same number of tile iterations (a CTA pair must stay in lock step); surplus tile indices
   // lie below the image: all loads zero-fill, nothing is stored
-  const int n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int n_units = (n_tiles + MT - 1) / MT;                   // a work unit = MT consecutive tiles
+  const int n_iter = (n_units + gridDim.x - 1) / gridDim.x;
   const int n_src = a.n_src;
   // Every CTA (pair) walks the (chunk, tap) sum in its own rotated order so that the 148 SMs do not all pull the
   // same weight tile out of L2 at the same moment (the accumulation order is free).
-  const int rot_id = CG2 ? blockIdx.x / 2 : blockIdx.x;
+  const int rot_id = (CG2 || MC2) ? blockIdx.x / 2 : blockIdx.x;      // a pair consumes weight stages in lock step
   const int rot_tap = rot_id % 9, rot_chunk = (rot_id / 9) % n_src;
 
   if (tid == 0) {
-    for (int i = 0; i < TC_NA; ++i) {
+    for (int i = 0; i < C::NA; ++i) {
       mbar_init(bar_a_full(i), CG2 ? 2 * TC_PROD : TC_PROD);   // CG2: the producers of both CTAs arrive at the leader
-      mbar_init(bar_a_empty(i), 1);
+      mbar_init(bar_a_empty(i), kTwoIssuers ? 2 : 1);      // one tcgen05.commit per MMA issuer warp
     }
     for (int i = 0; i < C::NB; ++i) {
       mbar_init(bar_b_full(i), 1);
-      mbar_init(bar_b_empty(i), 1);
+      mbar_init(bar_b_empty(i), MC2 ? 2 : 1);      // MC2: both CTAs must have consumed a stage before it is refilled
       mbar_init(bar_b_peer(i), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_acc_full(i), 1);
+    for (int i = 0; i < C::NACC; ++i) {
+      mbar_init(bar_acc_full(i), kTwoIssuers ? 2 : 1);
       mbar_init(bar_acc_empty(i), CG2 ? 512 : 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,28 +196,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   }
   tc_fence_before();
   __syncthreads();
-  if (CG2) cluster_sync_all();       // barriers of both CTAs are initialised before any remote arrive / multicast
+  if (CG2 || MC2) cluster_sync_all();       // barriers of both CTAs are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // optional role profiling (a.prof != null): cycles CTA 0 spends in each barrier wait, per role
+  long long prof_acc[4] = {0, 0, 0, 0};
+  const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
+  const long long prof_t0 = clock64();
+  auto pwait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (prof_on) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      prof_acc[slot] += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
   // arrive on a barrier that lives in the leader CTA
   auto arrive_leader = [&](uint32_t bar) {
     if (!CG2 || rank == 0) mbar_arrive(bar);
     else mbar_arrive_cluster(bar, 0);
   };
 
-  if (warp >= TC_W_APROD) {
+  // Everything above (barriers, TMEM, delta-head constants) and the weight stream below touch only constants; the
+  // activations belong to the previous kernel of the chain: wait for it here (PDL), except in the weight producer.
+  if (warp != TC_W_BPROD) pdl_wait();
+
+  if (warp >= TC_W_APROD && warp < TC_W_MMA2) {
     // ================= A producers =================
     const int pt = tid - TC_W_APROD * 32;
     const int p_hx = pt >> 3, p_g = pt & 7;          // this thread's halo column and k-group (pt < 80)
     int seq = 0;           // chunk sequence number over all tiles of this CTA
-    int pending = -1;      // stage whose loads were issued but not yet published
+    // up to INFLIGHT chunks are in flight: chunk i is published (its barrier arrived on) when chunk i+INFLIGHT-1 has been
+    // issued, so the copy latency is overlapped INFLIGHT-fold
+    constexpr int INFLIGHT = C::NA - 1;
+    int n_issued = 0, n_published = 0;
     for (int it = 0; it < n_iter; ++it) {
-      const int tile = it * gridDim.x + blockIdx.x;
-      const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
-      for (int ci = 0; ci < n_src; ++ci, ++seq) {
+      const int tile0 = (it * gridDim.x + blockIdx.x) * MT;
+      for (int cj = 0; cj < n_src * MT; ++cj, ++seq) {
+        const int ci = cj / MT, tile = tile0 + cj % MT;          // chunk-major: (chunk 0: tile 0, tile 1), (chunk 1: ...)
+        const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
         const int c = (ci + rot_chunk) % n_src;
-        const int st = seq % TC_NA;
-        mbar_wait(bar_a_empty(st), ((seq / TC_NA) & 1) ^ 1);
+        const int st = seq % C::NA;
+        pwait(bar_a_empty(st), ((seq / C::NA) & 1) ^ 1, 0);
         const uint32_t dst0 = sA + st * TC_A_BYTES;
         if (c == a.dn_chunk) {
           // disparity-neighbourhood encoder: channel k = 100 * (disp(y+k/7-3, x+k%7-3) - disp(y, x)), zero padded.
@@ -219,19 +285,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (pending >= 0) {   // publish the previous chunk while this one is in flight
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        ++n_issued;
+        if (n_issued - n_published >= INFLIGHT) {   // publish the oldest chunk while the newer ones are in flight
+          asm volatile("cp.async.wait_group %0;" ::"n"(INFLIGHT - 1) : "memory");
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          arrive_leader(bar_a_full(pending));
+          arrive_leader(bar_a_full(n_published % C::NA));
+          ++n_published;
         }
-        pending = st;
       }
     }
-    if (pending >= 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      arrive_leader(bar_a_full(pending));
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (; n_published < n_issued; ++n_published) arrive_leader(bar_a_full(n_published % C::NA));
   } else if (warp == TC_W_BPROD) {
     // ================= B producer =================
     if (lane == 0) {
@@ -248,29 +313,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           for (int si = 0; si < n_steps; ++si, ++seq) {
             const int s = ((si / 9 + rot_chunk) % n_src) * 9 + (si % 9 + rot_tap) % 9;
             const int st = seq % C::NB;
-            mbar_wait(bar_b_empty(st), ((seq / C::NB) & 1) ^ 1);
+            pwait(bar_b_empty(st), ((seq / C::NB) & 1) ^ 1, 0);
+            if (CG2) {
+              // each CTA fetches its half of the output channels with a TMA tensor load that credits the LEADER's
+              // barrier (cta_group::2): the leader arms it for both halves, no software relay between the CTAs
+              if (rank == 0) mbar_expect_tx(bar_b_full(st), 2 * C::B_BYTES);
+              tma2d_cg2(sB + st * C::B_BYTES, &wmap, 0, (s * 2 + (int)rank) * (C::B_BYTES / 256), bar_b_full(st));
+              continue;
+            }
             mbar_expect_tx(bar_b_full(st), C::B_BYTES);
-            // CG2: this CTA's half of the output channels is one contiguous slice of the pair layout
-            bulk_g2s(sB + st * C::B_BYTES, wsrc + ((size_t)s * (CG2 ? 2 : 1) + rank) * C::B_BYTES, C::B_BYTES,
-                     bar_b_full(st));
+            if (MC2) {
+              // my half of the tile goes to both CTAs (same offset), the peer sends the other half
+              constexpr uint32_t HALF = C::B_BYTES / 2;
+              bulk_g2s_mc(sB + st * C::B_BYTES + rank * HALF, wsrc + (size_t)s * C::B_BYTES + rank * HALF, HALF,
+                          bar_b_full(st), (uint16_t)3);
+            } else {
+              // CG2: this CTA's half of the output channels is one contiguous slice of the pair layout
+              bulk_g2s(sB + st * C::B_BYTES, wsrc + ((size_t)s * (CG2 ? 2 : 1) + rank) * C::B_BYTES, C::B_BYTES,
+                       bar_b_full(st));
+            }
           }
         }
       }
     }
-  } else if (warp == TC_W_MMA) {
-    // ================= MMA issuer (CG2: leader CTA only; the peer's warp relays its weight barriers) =================
-    if (lane == 0 && (!CG2 || rank == 0)) {
+  } else if (warp == TC_W_MMA || (kTwoIssuers && warp == TC_W_MMA2)) {
+    // ================= MMA issuers =================
+    // Two warps take alternate (chunk, tap) steps: waiting on the stage barrier, building descriptors and issuing four
+    // UTCHMMA + commit costs one thread ~790 cycles per step, the four MMAs only 384 -- a single issuer leaves the tensor
+    // pipe half idle.  MMAs of both warps accumulate into the same TMEM tile (the sum is order-free); only the
+    // step that starts a tile (accumulate = 0) must be issued first: its owner signals the other warp (named barrier 3).
+    // CG2: leader CTA only.
+    if (!CG2 || rank == 0) {     // each warp runs its loop converged (uniform control flow); one elected lane issues
       constexpr uint32_t idesc = umma_idesc(CG2 ? 256 : 128, N);
+      const int mw = warp == TC_W_MMA ? 0 : 1;
       int aseq = 0, bseq = 0;
       for (int t = 0; t < n_iter; ++t) {
-        const int as = t & 1;
-        mbar_wait(bar_acc_empty(as), ((t >> 1) & 1) ^ 1);     // epilogue(s) have drained this accumulator
+        const int as = t % C::NACC;
+        pwait(bar_acc_empty(as), ((t / C::NACC) & 1) ^ 1, 0);     // epilogue(s) have drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * N;
-        for (int c = 0; c < n_src; ++c, ++aseq) {
-          const int ast = aseq % TC_NA;
-          mbar_wait(bar_a_full(ast), (aseq / TC_NA) & 1);
+        const uint32_t d_tmem = tmem_base + as * (MT * N);
+        const bool own_first = !kTwoIssuers || (bseq & 1) == mw;   // do I issue the tile's first step?
+        bool ordered = !kTwoIssuers;
+        for (int c = 0; c < n_src; ++c, aseq += MT) {
+          int ast[MT];
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            ast[j] = (aseq + j) % C::NA;
+            pwait(bar_a_full(ast[j]), ((aseq + j) / C::NA) & 1, 1);
+          }
           for (int ti = 0; ti < 9; ++ti, ++bseq) {
+            if (kTwoIssuers && (bseq & 1) != mw) continue;         // the other issuer's step
             const int tap = C::RESIDENT ? ti : (ti + rot_tap) % 9;
             int bst;
             if (C::RESIDENT) {
@@ -278,58 +370,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
               if (t == 0) mbar_wait(bar_b_full(bst), 0);
             } else {
               bst = bseq % C::NB;
-              mbar_wait(bar_b_full(bst), (bseq / C::NB) & 1);
-              if (CG2) mbar_wait(bar_b_peer(bst), (bseq / C::NB) & 1);   // the peer's half has landed too
+              pwait(bar_b_full(bst), (bseq / C::NB) & 1, 2);         // CG2: armed for both CTAs' halves
+            }
+            if (!own_first && !ordered) {                          // the accumulate = 0 step has been issued
+              asm volatile("bar.sync %0, 64;" ::"r"(3 + (t & 1)) : "memory");     // ids alternate: issuers are <= 1 tile apart
+              ordered = true;
             }
             tc_fence_after();
             const int ky = tap / 3, kx = tap % 3;
             // descriptors of the 4 K=16 slices differ only in the start-address field: one 64-bit add each
-            const uint64_t ad0 = umma_desc(sA + ast * TC_A_BYTES + (ky * TC_HW + kx) * 16, TC_A_LBO, TC_A_SBO);
             const uint64_t bd0 = umma_desc(sB + bst * C::B_BYTES, C::NLOC * 16, 128);
+            const long long t_issue0 = prof_on ? clock64() : 0;
+            if (elect_one()) {
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-              const uint64_t ad = ad0 + (uint64_t)((2 * k16 * TC_A_LBO) >> 4);
-              const uint64_t bd = bd0 + (uint64_t)((2 * k16 * (C::NLOC * 16)) >> 4);
-              const uint32_t accum = (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u;
-              if (CG2) tc_mma2_f16(d_tmem, ad, bd, idesc, accum);
-              else tc_mma_f16(d_tmem, ad, bd, idesc, accum);
+              for (int j = 0; j < MT; ++j) {           // every M tile of the unit consumes this weight stage
+                const uint64_t ad0 = umma_desc(sA + ast[j] * TC_A_BYTES + (ky * TC_HW + kx) * 16, TC_A_LBO, TC_A_SBO);
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  const uint64_t ad = ad0 + (uint64_t)((2 * k16 * TC_A_LBO) >> 4);
+                  const uint64_t bd = bd0 + (uint64_t)((2 * k16 * (C::NLOC * 16)) >> 4);
+                  const uint32_t accum = (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u;
+                  if (CG2) tc_mma2_f16(d_tmem + j * N, ad, bd, idesc, accum);
+                  else tc_mma_f16(d_tmem + j * N, ad, bd, idesc, accum);
+                }
+              }
+              if (!C::RESIDENT) {            // stage free (in both CTAs) once these MMAs have read it
+                if (CG2) tc_commit2_mc(bar_b_empty(bst));
+                else if (MC2) tc_commit1_mc(bar_b_empty(bst), (uint16_t)3);
+                else tc_commit(bar_b_empty(bst));
+              }
             }
-            if (!C::RESIDENT) {            // stage free (in both CTAs) once these MMAs have read it
-              if (CG2) tc_commit2_mc(bar_b_empty(bst));
-              else tc_commit(bar_b_empty(bst));
+            __syncwarp();
+            if (own_first && !ordered) {                           // let the other issuer start on this tile
+              asm volatile("bar.arrive %0, 64;" ::"r"(3 + (t & 1)) : "memory");
+              ordered = true;
+            }
+            if (prof_on) prof_acc[3] += clock64() - t_issue0;
+          }
+          if (elect_one()) {                                       // my MMAs on this chunk's A stage(s)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              if (CG2) tc_commit2_mc(bar_a_empty(ast[j]));
+              else tc_commit(bar_a_empty(ast[j]));
             }
           }
-          if (CG2) tc_commit2_mc(bar_a_empty(ast));
-          else tc_commit(bar_a_empty(ast));
+          __syncwarp();
         }
-        if (CG2) tc_commit2_mc(bar_acc_full(as));             // accumulators complete (each CTA drains its own TMEM)
-        else tc_commit(bar_acc_full(as));
-      }
-    } else if (CG2 && rank == 1 && lane < C::NB) {
-      // peer CTA: forward "my half of weight stage `lane` has landed" to the leader; one lane per ring stage so that
-      // NB remote arrives are in flight (a remote arrive costs far more than one MMA step)
-      const int total_steps = n_iter * n_src * 9;
-      for (int bseq = lane; bseq < total_steps; bseq += C::NB) {
-        mbar_wait(bar_b_full(lane), (bseq / C::NB) & 1);
-        mbar_arrive_cluster(bar_b_peer(lane), 0);
+        if (elect_one()) {
+          if (CG2) tc_commit2_mc(bar_acc_full(as));           // my share of the accumulation is complete
+          else tc_commit(bar_acc_full(as));
+        }
+        __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ================= epilogue: thread = one pixel, half of the N channels =================
     // warps w and w+4 share TMEM lane quadrant w (a warp may only touch lanes 32*(warp%4)..+31) and split the columns
     const int quad = warp & 3, chalf = warp >> 2;
     const int m = quad * 32 + lane;                 // row of the M tile = TMEM lane
     const int r = m >> 3, cc = m & 7;
     for (int t = 0; t < n_iter; ++t) {
-      const int tile = t * gridDim.x + blockIdx.x;
-      const int as = t & 1;
+      const int as = t % C::NACC;
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+      const int tile = (t * gridDim.x + blockIdx.x) * MT + j;
       const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
-      mbar_wait(bar_acc_full(as), (t >> 1) & 1);
-      tc_fence_after();
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * N;
       const int yy = y0 + r, xx = x0 + cc;
       const bool ok = yy < a.h && xx < a.w;
       const long long p = ok ? (long long)yy * a.w + xx : 0;
+      // operands of the element-wise GRU algebra do not depend on the accumulator: fetch them before waiting for it
+      uint4 pre_a[4];
+      if (EPI == EPI_GATES && ok) ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);   // net slice of this thread's r chunk
+      if (j == 0) pwait(bar_acc_full(as), (t / C::NACC) & 1, 0);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * N) + j * N;
       float t9[9];
       if (EPI == EPI_DELTA) {
 #pragma unroll
@@ -362,7 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           } else if (n0 < 128) {
             if (ok) {
               float nt[32];
-              ld_half32(a.net + p * 64 + (n0 - 64), nt);
+              unpack_half32(pre_a, nt);          // n0 - 64 == chalf * 32
 #pragma unroll
               for (int e = 0; e < 32; ++e) v[e] = h_round(fast_sigmoid(h_round(v[e]))) * nt[e];
               st_half32(a.rnet + p * 64 + (n0 - 64), v);
@@ -403,18 +517,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           }
         }
       }
-      tc_fence_before();
-      arrive_leader(bar_acc_empty(as));             // accumulator stage may be overwritten
+      if (j == MT - 1) {
+        tc_fence_before();
+        arrive_leader(bar_acc_empty(as));           // accumulator stage may be overwritten
+      }
       if (EPI == EPI_DELTA && ok) {   // two partial sums per pixel (one per column half), added by the consumer
 #pragma unroll
         for (int q = 0; q < 9; ++q) a.s9[(p * 2 + chalf) * 9 + q] = t9[q];
       }
+      }   // j
     }
   }
 
+  if (prof_on && (warp == 0 || warp == TC_W_MMA || warp == TC_W_BPROD || warp == TC_W_APROD)) {   // (first MMA issuer only)
+    const int role = warp == 0 ? 0 : warp == TC_W_MMA ? 1 : warp == TC_W_BPROD ? 2 : 3;   // epilogue, mma, b, a
+    for (int i = 0; i < 4; ++i) a.prof[role * 8 + i] = (unsigned long long)prof_acc[i];
+    a.prof[role * 8 + 7] = (unsigned long long)(clock64() - prof_t0);
+  }
   tc_fence_before();
   __syncthreads();
-  if (CG2) cluster_sync_all();     // no CTA leaves while its partner can still arrive on / read from its shared memory
+  if (CG2 || MC2) cluster_sync_all();     // no CTA leaves while its partner can still arrive on / write to its shared memory
   if (warp == TC_W_MMA) {
     if (CG2)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -426,20 +548,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
 }
 
 // ---- host ----------------------------------------------------------------------------------------
-// N = 192 / 256 run as CTA pairs (cta_group::2); the N = 64 convs keep their weights resident and stay 1-CTA.
-template <int N>
-constexpr bool use_cg2() { return N != 64; }
-
-static int g_cg2_enabled = 0;   // CTA pairs are opt-in (cer_set_conv_variant(1) / CER_CONV=tc2): the relayed
-                                // weight barriers currently cost more than the halved operand traffic saves
+// Pair modes apply to the N = 192 / 256 convs (weights streamed per tile); the N = 64 convs keep their weights resident.
+static int g_pair_mode = TC_SINGLE;   // TC_SINGLE / TC_CG2 / TC_MC2 / TC_MT2 for the streamed-weight convs (A/B switch)
 
 template <int N, int EPI>
 static int tc_configure_one() {
-  CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                TcCfg<N, false>::TOTAL));
-  if (use_cg2<N>())
-    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, use_cg2<N>()>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<N, use_cg2<N>()>::TOTAL));
+  CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, TC_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TcCfg<N, TC_SINGLE>::TOTAL));
+  if (N != 64) {
+    constexpr int M1 = N != 64 ? TC_CG2 : TC_SINGLE, M2 = N != 64 ? TC_MC2 : TC_SINGLE;
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<N, M1>::TOTAL));
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<N, M2>::TOTAL));
+    constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<N, M3>::TOTAL));
+  }
   return CER_OK;
 }
 
@@ -452,40 +577,98 @@ int tc_configure() {
   return CER_OK;
 }
 
-void tc_set_cg2(int enabled) { g_cg2_enabled = enabled; }
+void tc_set_pair_mode(int mode) { g_pair_mode = mode; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D byte view of the CTA-pair weight layout: rows of 256 B, one box = one CTA's half of a (chunk, tap) tile.
+static int make_weight_map(const void* base, size_t total_bytes, int half_bytes, CUtensorMap* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return CER_ERR_INVALID;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t gdim[2] = {256, (cuuint64_t)(total_bytes / 256)};
+  const cuuint64_t gstride[1] = {256};
+  const cuuint32_t box[2] = {256, (cuuint32_t)(half_bytes / 256)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CER_ERR_INVALID;
+  }
+  return CER_OK;
+}
+
+template <int N, int EPI, int MODE>
+static int launch_pair(const ConvArgs& a, int tiles, int kind, cudaStream_t stream) {
+  CUtensorMap wmap;
+  memset(&wmap, 0, sizeof(wmap));
+  if (MODE == TC_CG2) {
+    int rc = make_weight_map(a.wtc2, (size_t)a.n_src * 9 * 64 * N * 2, TcCfg<N, MODE>::B_BYTES, &wmap);
+    if (rc) return rc;
+  }
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  grid &= ~1;                                             // whole CTA pairs
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TcCfg<N, MODE>::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cer::g_pdl ? 2 : 1;
+  if (cer::g_timer) cer::timer_begin(kind, stream);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<N, EPI, MODE>, a, wmap);
+  if (cer::g_timer) cer::timer_end(stream);
+  ++cer::g_launches;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("conv3x3_tc (cta pair) launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return check_launch("conv3x3_tc");
+}
 
 template <int N, int EPI>
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = ((a.w + TC_TW - 1) / TC_TW) * ((a.h + TC_TH - 1) / TC_TH);
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
-  if (use_cg2<N>() && g_cg2_enabled && tiles >= 2) {
-    int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    grid &= ~1;                                             // whole CTA pairs
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TcCfg<N, use_cg2<N>()>::TOTAL;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cer::g_timer) cer::timer_begin(kind, stream);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<N, EPI, use_cg2<N>()>, a);
-    if (cer::g_timer) cer::timer_end(stream);
-    ++cer::g_launches;
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("conv3x3_tc (cta pair) launch failed: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
+  if (N != 64 && tiles >= 2 && g_pair_mode == TC_MT2) {
+    constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
+    const int units = (tiles + 1) / 2;
+    const int grid = units < kNumSMs ? units : kNumSMs;
+    CUtensorMap nomap;
+    memset(&nomap, 0, sizeof(nomap));
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, TC_THREADS, (TcCfg<N, M3>::TOTAL), stream, a, nomap);
     return check_launch("conv3x3_tc");
   }
+  if (N != 64 && tiles >= 2 && g_pair_mode != TC_SINGLE) {
+    constexpr int M1 = N != 64 ? TC_CG2 : TC_SINGLE, M2 = N != 64 ? TC_MC2 : TC_SINGLE;
+    return g_pair_mode == TC_CG2 ? launch_pair<N, EPI, M1>(a, tiles, kind, stream)
+                                 : launch_pair<N, EPI, M2>(a, tiles, kind, stream);
+  }
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
-  CER_LAUNCH(kind, (conv3x3_tc_kernel<N, EPI, false>), grid, TC_THREADS, (TcCfg<N, false>::TOTAL), stream, a);
+  CUtensorMap nomap;
+  memset(&nomap, 0, sizeof(nomap));
+  CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, TC_SINGLE>), grid, TC_THREADS, (TcCfg<N, TC_SINGLE>::TOTAL), stream, a,
+                 nomap);
   return check_launch("conv3x3_tc");
 }
 

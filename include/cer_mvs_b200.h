@@ -122,11 +122,18 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     const float* corr, int slots, float* delta, int apply_delta, int stage, int h, int w,
                     cer_stream_t stream);
 
-/* Which tensor-core path the 3x3 convolutions use: 2 = tcgen05.mma + TMEM, one CTA per SM (default);
- * 1 = the same with CTA pairs (cta_group::2, M = 256) for the N >= 192 convolutions (CER_CONV=tc2, experimental);
- * 0 = mma.sync (the v1 kernels, kept for A/B validation; CER_CONV=hmma).  Takes effect for launches and
- * graph captures issued afterwards. */
+/* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on all of them):
+ *   2 = tcgen05.mma + TMEM, persistent CTAs, one 128-pixel tile per CTA at a time (default; CER_CONV unset)
+ *   1 = the N >= 192 convolutions as CTA pairs issuing cta_group::2 MMAs (M = 256), weights by TMA tensor loads that
+ *       credit the leader's barrier (CER_CONV=tc2)
+ *   3 = the N >= 192 convolutions as 2-CTA clusters that multicast each weight tile
+ *   4 = the N >= 192 convolutions with two 128-pixel tiles per CTA sharing each weight stage
+ *   0 = mma.sync (the v1 kernels; CER_CONV=hmma).
+ * Takes effect for launches and graph captures issued afterwards. */
 int cer_set_conv_variant(int variant);
+
+/* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */
+int cer_debug_set_conv_profile(void* dev_buf);
 
 /* ConvGRU.forward alone (core/update.py:17-25): net [h*w,64] fp16 NHWC updated in place from
  * inputs inp [h*w,64], dn [h*w,64] (49 disparity-encoder channels + 15 zero), e [h*w,64], all fp16 NHWC. */
