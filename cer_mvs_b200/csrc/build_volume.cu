@@ -216,6 +216,141 @@ __global__ void __launch_bounds__(256) build_volume_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp16 features, 4 lanes per pixel: every lane owns 16 channels and fetches them with ONE 256-bit load
+// (LDG.E.256, sm_100), so a warp instruction still covers 8 full 128-byte rows (one L1 wavefront per row) but the
+// per-sample bookkeeping is shared by 4 lanes instead of 8 and there are half as many load instructions.
+// ------------------------------------------------------------------------------------------
+struct Slice16 {
+  uint32_t v[8];
+  __device__ __forceinline__ void load(const void* p) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+  }
+  __device__ __forceinline__ float dot(const Slice16& o) const {
+    float d = fhfma_lo(v[0], o.v[0], 0.f);
+    d = fhfma_hi(v[0], o.v[0], d);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      d = fhfma_lo(v[i], o.v[i], d);
+      d = fhfma_hi(v[i], o.v[i], d);
+    }
+    return d;
+  }
+};
+
+constexpr int kH16Chunks = 4;   // chunks of 4 hypotheses per block in sequence
+
+__global__ void __launch_bounds__(256) build_volume_h16_kernel(
+    const __half* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
+    const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
+    float lo_origin, float* __restrict__ origin_out, float* __restrict__ volume, float out_scale, int per_view,
+    int h, int w) {
+  __shared__ float sP[kMaxPairs][12];
+  __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
+  __shared__ __align__(16) int sS[64 * 4 * 8];   // per 4-lane group: 4 samples x {4 byte offsets, 4 weights}
+  for (int t = threadIdx.x; t < n_pairs * 12; t += blockDim.x) sP[t / 12][t % 12] = Pij[(t / 12) * 16 + (t % 12)];
+  for (int t = threadIdx.x; t < n_pairs; t += blockDim.x) {
+    sI[t] = ii[t];
+    sJ[t] = jj[t];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 3;
+  const long long px = (long long)h * w;
+  // a block = an 8 x 8 pixel tile (a warp = one tile row): neighbouring pixels sample neighbouring source pixels at the
+  // same hypothesis, so a 2-D tile re-uses corner rows in both directions out of L1 (the kernel is bound by L1 misses)
+  const int tiles_x = (w + 7) >> 3;
+  const int pl = threadIdx.x >> 2;
+  const int x_ = (blockIdx.x % tiles_x) * 8 + (pl & 7), y_ = (blockIdx.x / tiles_x) * 8 + (pl >> 3);
+  const bool valid = x_ < w && y_ < h;
+  const int x = valid ? x_ : w - 1, y = valid ? y_ : h - 1;
+  const long long p = (long long)y * w + x;
+  const float xf = (float)x, yf = (float)y;
+  const float din = __ldg(disp_in + p);
+  const float org = shift ? (din < lo_origin ? lo_origin : din) : din;      // core/corr.py:59-63
+  if (valid && lane == 0 && blockIdx.y == 0) origin_out[p] = org;
+
+  const long long img_stride = px * kFeatC;
+  int cached_ref = -1;
+  Slice16 f1;
+  int* grp = sS + (threadIdx.x >> 2) * 32;
+
+  const int chunk0 = blockIdx.y * kH16Chunks;
+  for (int ch = chunk0; ch < chunk0 + kH16Chunks; ++ch) {
+    const int d0 = ch * 4;
+    if (d0 >= D) break;
+    const int d = d0 + lane;
+    const float dval = __fadd_rn(__fmul_rn((float)(min(d, D - 1) - D / 2), incre), org);   // corr.py:56,66
+    float acc = 0.f;
+    for (int k = 0; k < n_pairs; ++k) {
+      const int ri = sI[k];
+      if (ri != cached_ref) {
+        f1.load(feats + ri * img_stride + p * kFeatC + lane * 16);
+        cached_ref = ri;
+      }
+      const __half* img2 = feats + sJ[k] * img_stride + lane * 16;
+      const float* P = sP[k];
+      const float X0 = fmaf(P[3], dval, fmaf(P[1], yf, P[0] * xf) + P[2]);
+      const float X1 = fmaf(P[7], dval, fmaf(P[5], yf, P[4] * xf) + P[6]);
+      const float X2 = fmaf(P[11], dval, fmaf(P[9], yf, P[8] * xf) + P[10]);
+      float u = __fdiv_rn(X0, X2), v = __fdiv_rn(X1, X2);
+      u = u < -1e4f ? -1e4f : (u > 1e4f ? 1e4f : u);
+      v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
+      const float fu = floorf(u), fv = floorf(v);
+      const float dx = u - fu, dy = v - fv;
+      const int ix = (int)fu, iy = (int)fv;
+      {
+        const int y0c = min(max(iy, 0), h - 1), y1c = min(max(iy + 1, 0), h - 1);
+        const int x0c = min(max(ix, 0), w - 1), x1c = min(max(ix + 1, 0), w - 1);
+        const float wy0 = (iy >= 0 && iy < h) ? 1.f - dy : ((dy != dy) ? dy : 0.f);
+        const float wy1 = (iy + 1 >= 0 && iy + 1 < h) ? dy : ((dy != dy) ? dy : 0.f);
+        const float wx0 = (ix >= 0 && ix < w) ? 1.f - dx : ((dx != dx) ? dx : 0.f);
+        const float wx1 = (ix + 1 >= 0 && ix + 1 < w) ? dx : ((dx != dx) ? dx : 0.f);
+        int4* slot = reinterpret_cast<int4*>(grp + lane * 8);
+        slot[0] = make_int4((y0c * w + x0c) * 128, (y0c * w + x1c) * 128, (y1c * w + x0c) * 128, (y1c * w + x1c) * 128);
+        reinterpret_cast<float4*>(slot)[1] = make_float4(wy0, wy1, wx0, wx1);
+      }
+      __syncwarp();
+      float part[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int4 o4 = *reinterpret_cast<const int4*>(grp + s * 8);
+        const float4 wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
+        Slice16 f2;
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.x));
+        const float d00 = f1.dot(f2);
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.y));
+        const float d01 = f1.dot(f2);
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.z));
+        const float d10 = f1.dot(f2);
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.w));
+        const float d11 = f1.dot(f2);
+        part[s] = ((d00 * wt.x) * wt.z + (d01 * wt.x) * wt.w) + ((d10 * wt.y) * wt.z + (d11 * wt.y) * wt.w);
+      }
+      __syncwarp();
+      // butterfly over the 4 lanes: lane L ends with the total of sample L
+      float k2[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = (lane & 2) ? part[i] : part[i + 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        k2[i] = ((lane & 2) ? part[i + 2] : part[i]) + recv;
+      }
+      const float send = (lane & 1) ? k2[0] : k2[1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      const float total = ((lane & 1) ? k2[1] : k2[0]) + recv;
+      if (per_view) {
+        if (valid && d < D) volume[((long long)k * px + p) * D + d] = total * out_scale;
+      } else {
+        acc += total;
+      }
+    }
+    if (!per_view && valid && d < D) volume[p * D + d] = acc * out_scale;
+  }
+}
+
 }  // namespace cer
 
 namespace cer {
@@ -226,7 +361,7 @@ static int g_build_variant = -1;
 static int build_variant() {
   if (g_build_variant < 0) {
     const char* e = getenv("CER_BUILD");
-    g_build_variant = (e && !strcmp(e, "tc")) ? 1 : 0;
+    g_build_variant = (e && !strcmp(e, "tc")) ? 1 : (e && !strcmp(e, "l8")) ? 2 : 0;
   }
   return g_build_variant;
 }
@@ -235,7 +370,8 @@ static int build_variant() {
 using namespace cer;
 
 extern "C" int cer_set_build_variant(int variant) {
-  CER_REQUIRE(variant == 0 || variant == 1, "cer_set_build_variant: 0 (FHFMA gather kernel) or 1 (tcgen05 gather kernel)");
+  CER_REQUIRE(variant >= 0 && variant <= 2,
+              "cer_set_build_variant: 0 FHFMA gather, 4 lanes x 256-bit loads (default); 1 tcgen05 gather; 2 FHFMA gather, 8 lanes");
   g_build_variant = variant;
   return CER_OK;
 }
@@ -255,7 +391,11 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   const long long px = (long long)h * w;
   const int chunks = ceil_div(D, 8);
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
-  if (feats_f16)
+  if (feats_f16 && build_variant() != 2) {
+    dim3 g16(((w + 7) / 8) * ((h + 7) / 8), ceil_div(ceil_div(D, 4), kH16Chunks));
+    CER_LAUNCH(KK_BUILD, build_volume_h16_kernel, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
+               shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+  } else if (feats_f16)
     CER_LAUNCH(KK_BUILD, build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
                shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
   else

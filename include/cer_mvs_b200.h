@@ -76,9 +76,9 @@ int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const i
                      float* origin, float* volume, float out_scale, int per_view, int h, int w,
                      cer_stream_t stream);
 
-/* Kernel used for fp16 features: 0 = 8-lane gather + FHFMA mixed-precision FMA (default), 1 = cp.async gather
- * into UMMA tiles + tcgen05.mma (needs D >= 43).  Also selectable with CER_BUILD=tc.  fp32 features always
- * use variant 0 with plain FFMA. */
+/* Kernel used for fp16 features: 0 = 4-lane gather with 256-bit loads + FHFMA mixed-precision FMA (default),
+ * 2 = the same with 8 lanes x 128-bit loads (CER_BUILD=l8), 1 = cp.async gather into UMMA tiles + tcgen05.mma
+ * (needs D >= 43; CER_BUILD=tc).  fp32 features always use the 8-lane kernel with plain FFMA. */
 int cer_set_build_variant(int variant);
 
 /* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
