@@ -34,11 +34,13 @@ constexpr int TC_A_SBO = TC_HW * 16;           // bytes between 8-row groups (= 
 constexpr int TC_A_BYTES = 8 * TC_A_LBO;       // one 64-channel chunk: 23 040 B
 constexpr int TC_PROD = 96;                    // A producer threads (80 active: one per (halo column, k-group))
 constexpr int TC_W_MMA = 8, TC_W_BPROD = 9, TC_W_APROD = 10;   // warp roles; warps 0-7 are the epilogue
-constexpr int TC_W_MMA2 = TC_W_APROD + TC_PROD / 32;            // second MMA issuer (13)
-constexpr int TC_THREADS = (TC_W_MMA2 + 1) * 32;                // 448
+constexpr int TC_W_MMA2 = TC_W_APROD + TC_PROD / 32;            // warp 13: dn producer (or second MMA issuer, see kTwoIssuers)
+constexpr int TC_W_DN = TC_W_MMA2;                               // warps 13-15: dn producers
+constexpr int TC_DN = 96;                                        // dn producer threads (== TC_PROD: same arrival count)
+constexpr int TC_THREADS = TC_W_DN * 32 + TC_DN;                 // 512
 // Two issuer warps taking alternate (chunk, tap) steps buy ~5 % on the gate conv but make the fp32 accumulation order
 // (and therefore the last bit of some outputs) depend on how the two warps interleave: off, results are bit-reproducible.
-constexpr bool kTwoIssuers = false;
+constexpr bool kTwoIssuers = false;      // (warp 13 generates the dn chunk instead)
 constexpr int TC_DT_H = TC_HH + 6, TC_DT_W = TC_HW + 6;   // disparity tile for the 7x7 encoder: 24 x 16
 
 // CG2: the CTA pair of a 2-CTA cluster runs one M=256 tcgen05.mma.cta_group::2 per step: each CTA supplies its own
@@ -59,22 +61,42 @@ struct TcCfg {
   static constexpr bool MC2 = MODE == TC_MC2;
   static constexpr int MT = MODE == TC_MT2 ? 2 : 1;             // M tiles per CTA work unit
   static constexpr bool RESIDENT = (N == 64);                 // all 9 weight tiles stay in smem
-  static constexpr int NB = RESIDENT ? 9 : (CG2 ? (N == 256 ? 8 : 12) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
+  // taps per weight stage: the CTA-pair form moves a whole kernel row (3 taps) per stage so that the issuing thread
+  // pays one barrier wait + one commit per 12 MMAs instead of per 4 (its per-step cost, not the tensor pipe, bounds
+  // the streamed-weight convs); the pair's halved weight footprint is what makes room for it
+  static constexpr int TPS = CG2 ? 3 : 1;
+  static constexpr int NG = 9 / TPS;                          // stages per 64-channel chunk
+  static constexpr int NB = RESIDENT ? 9 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
   static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
   // A ring depth (64-channel chunks).  Deeper rings / more accumulator stages for the N = 64 convs were measured
   // slower (q/GRU 36 -> 44 us): those kernels are bound by their per-tile latency chain, not by ring capacity.
   static constexpr int NA = MT == 2 ? 4 : 3;
   static constexpr int NACC = MT == 2 ? 1 : 2;                    // TMEM accumulator stages (of MT x N columns)
-  static constexpr int B_BYTES = 64 * NLOC * 2;
+  static constexpr int B_BYTES = 64 * NLOC * 2;               // one tap
+  static constexpr int STAGE_BYTES = TPS * B_BYTES;
   static constexpr int TMEM_COLS = (NACC * MT * N <= 128) ? 128 : (NACC * MT * N <= 256 ? 256 : 512);
   static constexpr int OFF_B = NA * TC_A_BYTES;
-  static constexpr int OFF_EXTRA = OFF_B + NB * B_BYTES;                  // DELTA: w2 [9][256] f32 + bias [256] f32
-  static constexpr int EXTRA_BYTES = (N == 256) ? (9 * 256 + 256) * 4 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
+  static constexpr int OFF_EXTRA = OFF_B + NB * STAGE_BYTES;                  // DELTA: bias [256] f32 + w2 [9][256] f16; GATES: disparity tile
+  static constexpr int EXTRA_BYTES = (N == 256) ? 256 * 4 + 9 * 256 * 2 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
   static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
   static constexpr int NUM_BAR = 2 * NA + 3 * NB + 2 * NACC;  // a_full/empty, b_full/empty/peer_full, acc_full/empty
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
+
+// Blackwell mixed-precision FMA (PTX fma.rn.f32.f16 -> SASS FHFMA): exact fp16 x fp16 product, fp32 accumulate
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {
+  float r;
+  asm("{\n .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n fma.rn.f32.f16 %0, al, bl, %3;\n}"
+      : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
+  float r;
+  asm("{\n .reg .b16 al, ah, bl, bh;\n mov.b32 {al, ah}, %1;\n mov.b32 {bl, bh}, %2;\n fma.rn.f32.f16 %0, ah, bh, %3;\n}"
+      : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -135,6 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   static_assert(MT == 1 || (!C::RESIDENT && N * 2 <= 512), "MT2 is for the streamed-weight convs");
   static_assert(!(MC2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
   static_assert(!(CG2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
+  static_assert(!CG2 || C::NB >= C::NA, "the CTA pair reuses bar_b_peer(0..NA) as peer-A-full barriers");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s0 = smem_u32(smem);
   const uint32_t sA = s0, sB = s0 + C::OFF_B, sBar = s0 + C::OFF_BAR;
@@ -160,11 +183,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   // Every CTA (pair) walks the (chunk, tap) sum in its own rotated order so that the 148 SMs do not all pull the
   // same weight tile out of L2 at the same moment (the accumulation order is free).
   const int rot_id = (CG2 || MC2) ? blockIdx.x / 2 : blockIdx.x;      // a pair consumes weight stages in lock step
-  const int rot_tap = rot_id % 9, rot_chunk = (rot_id / 9) % n_src;
+  const int rot_g = rot_id % C::NG, rot_chunk = (rot_id / C::NG) % n_src;
 
   if (tid == 0) {
     for (int i = 0; i < C::NA; ++i) {
-      mbar_init(bar_a_full(i), CG2 ? 2 * TC_PROD : TC_PROD);   // CG2: the producers of both CTAs arrive at the leader
+      mbar_init(bar_a_full(i), TC_PROD);   // local producers; CG2: the peer relays its completions to bar_b_peer(i)
       mbar_init(bar_a_empty(i), kTwoIssuers ? 2 : 1);      // one tcgen05.commit per MMA issuer warp
     }
     for (int i = 0; i < C::NB; ++i) {
@@ -190,9 +213,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
     }
   }
   if (EPI == EPI_DELTA && warp < 8) {
-    float* ex = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
-    for (int i = tid; i < 9 * 256; i += 256) ex[i] = __ldg(a.w2 + i);
-    for (int i = tid; i < 256; i += 256) ex[9 * 256 + i] = __ldg(a.bias + i);
+    // delta head constants: bias f32 [256], then the 3x3 -> 1 weights as fp16 [9][256] (the packed values are
+    // fp16-representable, so the conversion is exact)
+    float* exb = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
+    __half* exw = reinterpret_cast<__half*>(smem + C::OFF_EXTRA + 256 * 4);
+    for (int i = tid; i < 256; i += 256) exb[i] = __ldg(a.bias + i);
+    for (int i = tid; i < 9 * 256; i += 256) exw[i] = __float2half_rn(__ldg(a.w2 + i));
   }
   tc_fence_before();
   __syncthreads();
@@ -227,10 +253,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
     const int pt = tid - TC_W_APROD * 32;
     const int p_hx = pt >> 3, p_g = pt & 7;          // this thread's halo column and k-group (pt < 80)
     int seq = 0;           // chunk sequence number over all tiles of this CTA
-    // up to INFLIGHT chunks are in flight: chunk i is published (its barrier arrived on) when chunk i+INFLIGHT-1 has been
-    // issued, so the copy latency is overlapped INFLIGHT-fold
-    constexpr int INFLIGHT = C::NA - 1;
-    int n_issued = 0, n_published = 0;
+    // A stage is published by the hardware: every producer thread attaches a cp.async.mbarrier.arrive.noinc to its
+    // copies, so the producers never wait for (or fence) their own copies and run ahead of the MMA by the ring depth.
+    // (A producer-side wait_group + fence.proxy.async serialises on the copies of the NEXT chunk too: measured, the
+    // producers then became the critical path of the CTA-pair form.)  The MMA warp issues the generic->async proxy
+    // fence after it has observed the barrier.
     for (int it = 0; it < n_iter; ++it) {
       const int tile0 = (it * gridDim.x + blockIdx.x) * MT;
       for (int cj = 0; cj < n_src * MT; ++cj, ++seq) {
@@ -240,35 +267,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
         const int st = seq % C::NA;
         pwait(bar_a_empty(st), ((seq / C::NA) & 1) ^ 1, 0);
         const uint32_t dst0 = sA + st * TC_A_BYTES;
+        const long long t_fill0 = prof_on ? clock64() : 0;
         if (c == a.dn_chunk) {
-          // disparity-neighbourhood encoder: channel k = 100 * (disp(y+k/7-3, x+k%7-3) - disp(y, x)), zero padded.
-          // Stage the 24 x 16 disparity tile once, then one thread per halo pixel writes its 8 k-groups.
-          float* sD = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
-          asm volatile("bar.sync 1, 96;" ::: "memory");           // previous tile's readers are done
-          for (int i = pt; i < TC_DT_H * TC_DT_W; i += TC_PROD) {
-            const int yy = y0 - 4 + i / TC_DT_W, xx = x0 - 4 + i % TC_DT_W;
-            sD[i] = (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) ? __ldg(a.disp + (long long)yy * a.w + xx) : 0.f;
-          }
-          asm volatile("bar.sync 1, 96;" ::: "memory");
-          for (int hp = pt; hp < TC_HPX; hp += TC_PROD) {
-            const int hy = hp / TC_HW, hx = hp % TC_HW;
-            const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
-            const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
-            const float* win = sD + hy * TC_DT_W + hx;             // window origin = (hy+3-3, hx+3-3)
-            const float ctr = win[3 * TC_DT_W + 3];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              __align__(16) __half v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int k = g * 8 + e;                           // compile-time after unrolling
-                float val = 0.f;
-                if (k < kDispEnc) val = __fmul_rn(100.f, __fsub_rn(win[(k / 7) * TC_DT_W + (k % 7)], ctr));
-                v[e] = __float2half_rn(ok ? val : 0.f);
-              }
-              *reinterpret_cast<uint4*>(smem + (dst0 - s0) + g * TC_A_LBO + hp * 16) = *reinterpret_cast<const uint4*>(v);
-            }
-          }
+          continue;       // generated by the dn warp below; the wait above keeps this warp in step with the ring phases
         } else if (p_hx < TC_HW) {
           // one halo column x one k-group per thread, walking down the 18 halo rows: 2 adds per copy
           const int xx = x0 - 1 + p_hx;
@@ -284,19 +285,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
             dst += TC_A_SBO;
           }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        ++n_issued;
-        if (n_issued - n_published >= INFLIGHT) {   // publish the oldest chunk while the newer ones are in flight
-          asm volatile("cp.async.wait_group %0;" ::"n"(INFLIGHT - 1) : "memory");
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          arrive_leader(bar_a_full(n_published % C::NA));
-          ++n_published;
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_a_full(st)) : "memory");
+        if (prof_on) prof_acc[3] += clock64() - t_fill0;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp >= TC_W_DN) {
+    // ================= dn producers (gate conv only) =================
+    // disparity-neighbourhood encoder (core/update.py:41-49), generated straight into the A ring: channel
+    // k = 100 * (disp(y + k/7 - 3, x + k%7 - 3) - disp(y, x)), zero padded.  Three warps of their own, off the copy
+    // warps' path: they stage the 24 x 16 disparity tile, then each thread writes the 8 k-groups of its halo pixels.
+    if (a.dn_chunk >= 0) {
+      static_assert(TC_DN == TC_PROD, "the dn threads stand in for the copy threads' arrivals on a_full");
+      float* sD = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
+      constexpr int DT = TC_DT_H * TC_DT_W, DT_PER = DT / TC_DN;   // 384 / 96 = 4 values per thread
+      static_assert(DT % TC_DN == 0, "disparity tile is spread evenly over the dn threads");
+      const int dt = tid - TC_W_DN * 32;
+      int seq = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int tile0 = (it * gridDim.x + blockIdx.x) * MT;
+        for (int cj = 0; cj < n_src * MT; ++cj, ++seq) {
+          const int ci = cj / MT, tile = tile0 + cj % MT;
+          const int st = seq % C::NA;
+          if ((ci + rot_chunk) % n_src != a.dn_chunk) {
+            // Not mine, but observe the release of EVERY ring use in order: a parity wait issued two phases ahead of
+            // the barrier would alias with the phase before and succeed at once.  Costs nothing: my next stage is
+            // released after this one anyway.
+            mbar_wait(bar_a_empty(st), ((seq / C::NA) & 1) ^ 1);
+            continue;
+          }
+          const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
+          float dv[DT_PER];                                        // in flight while we wait for the stage
+#pragma unroll
+          for (int q = 0; q < DT_PER; ++q) {
+            const int i = q * TC_DN + dt;
+            const int yy = y0 - 4 + i / TC_DT_W, xx = x0 - 4 + i % TC_DT_W;
+            dv[q] = (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) ? __ldg(a.disp + (long long)yy * a.w + xx) : 0.f;
+          }
+          pwait(bar_a_empty(st), ((seq / C::NA) & 1) ^ 1, 0);
+          const long long t_fill0 = prof_on ? clock64() : 0;
+          asm volatile("bar.sync 1, 96;" ::: "memory");            // previous tile's readers are done
+#pragma unroll
+          for (int q = 0; q < DT_PER; ++q) sD[q * TC_DN + dt] = dv[q];
+          asm volatile("bar.sync 1, 96;" ::: "memory");
+          unsigned char* dstp = smem + st * TC_A_BYTES;
+          for (int hp = dt; hp < TC_HPX; hp += TC_DN) {
+            const int hy = hp / TC_HW, hx = hp % TC_HW;
+            const int yy = y0 - 1 + hy, xx = x0 - 1 + hx;
+            const bool ok = yy >= 0 && yy < a.h && xx >= 0 && xx < a.w;
+            const float* win = sD + hy * TC_DT_W + hx;             // window origin = (hy+3-3, hx+3-3)
+            const float ctr = win[3 * TC_DT_W + 3];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              __align__(16) __half v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int k = g * 8 + e;                           // compile-time after unrolling
+                float val = 0.f;
+                if (k < kDispEnc) val = __fmul_rn(100.f, __fsub_rn(win[(k / 7) * TC_DT_W + (k % 7)], ctr));
+                v[e] = __float2half_rn(ok ? val : 0.f);
+              }
+              *reinterpret_cast<uint4*>(dstp + g * TC_A_LBO + hp * 16) = *reinterpret_cast<const uint4*>(v);
+            }
+          }
+          mbar_arrive(bar_a_full(st));       // plain stores, ordinary (release) arrival; the MMA warp fences the proxy
+          if (prof_on) prof_acc[2] += clock64() - t_fill0;
         }
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (; n_published < n_issued; ++n_published) arrive_leader(bar_a_full(n_published % C::NA));
   } else if (warp == TC_W_BPROD) {
     // ================= B producer =================
     if (lane == 0) {
@@ -308,28 +364,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
         }
       } else {
         int seq = 0;
-        const int n_steps = n_src * 9;
+        const int n_steps = n_src * C::NG;
         for (int it = 0; it < n_iter; ++it) {
           for (int si = 0; si < n_steps; ++si, ++seq) {
-            const int s = ((si / 9 + rot_chunk) % n_src) * 9 + (si % 9 + rot_tap) % 9;
+            const int s = ((si / C::NG + rot_chunk) % n_src) * 9 + ((si % C::NG + rot_g) % C::NG) * C::TPS;   // first tap
             const int st = seq % C::NB;
             pwait(bar_b_empty(st), ((seq / C::NB) & 1) ^ 1, 0);
             if (CG2) {
               // each CTA fetches its half of the output channels with a TMA tensor load that credits the LEADER's
               // barrier (cta_group::2): the leader arms it for both halves, no software relay between the CTAs
-              if (rank == 0) mbar_expect_tx(bar_b_full(st), 2 * C::B_BYTES);
-              tma2d_cg2(sB + st * C::B_BYTES, &wmap, 0, (s * 2 + (int)rank) * (C::B_BYTES / 256), bar_b_full(st));
+              if (rank == 0) mbar_expect_tx(bar_b_full(st), 2 * C::STAGE_BYTES);
+#pragma unroll
+              for (int kx = 0; kx < C::TPS; ++kx)
+                tma2d_cg2(sB + st * C::STAGE_BYTES + kx * C::B_BYTES, &wmap, 0,
+                          ((s + kx) * 2 + (int)rank) * (C::B_BYTES / 256), bar_b_full(st));
               continue;
             }
             mbar_expect_tx(bar_b_full(st), C::B_BYTES);
             if (MC2) {
               // my half of the tile goes to both CTAs (same offset), the peer sends the other half
               constexpr uint32_t HALF = C::B_BYTES / 2;
-              bulk_g2s_mc(sB + st * C::B_BYTES + rank * HALF, wsrc + (size_t)s * C::B_BYTES + rank * HALF, HALF,
+              bulk_g2s_mc(sB + st * C::STAGE_BYTES + rank * HALF, wsrc + (size_t)s * C::B_BYTES + rank * HALF, HALF,
                           bar_b_full(st), (uint16_t)3);
             } else {
               // CG2: this CTA's half of the output channels is one contiguous slice of the pair layout
-              bulk_g2s(sB + st * C::B_BYTES, wsrc + ((size_t)s * (CG2 ? 2 : 1) + rank) * C::B_BYTES, C::B_BYTES,
+              bulk_g2s(sB + st * C::STAGE_BYTES, wsrc + ((size_t)s * (CG2 ? 2 : 1) + rank) * C::B_BYTES, C::B_BYTES,
                        bar_b_full(st));
             }
           }
@@ -360,13 +419,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           for (int j = 0; j < MT; ++j) {
             ast[j] = (aseq + j) % C::NA;
             pwait(bar_a_full(ast[j]), ((aseq + j) / C::NA) & 1, 1);
+            if (CG2) pwait(bar_b_peer(ast[j]), ((aseq + j) / C::NA) & 1, 1);   // the peer CTA's half of the pixel rows
           }
-          for (int ti = 0; ti < 9; ++ti, ++bseq) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // producers' cp.async / st.shared -> UMMA reads
+          for (int ti = 0; ti < C::NG; ++ti, ++bseq) {
             if (kTwoIssuers && (bseq & 1) != mw) continue;         // the other issuer's step
-            const int tap = C::RESIDENT ? ti : (ti + rot_tap) % 9;
+            const int g = C::RESIDENT ? ti : (ti + rot_g) % C::NG;
             int bst;
             if (C::RESIDENT) {
-              bst = tap;
+              bst = g;
               if (t == 0) mbar_wait(bar_b_full(bst), 0);
             } else {
               bst = bseq % C::NB;
@@ -377,21 +438,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
               ordered = true;
             }
             tc_fence_after();
-            const int ky = tap / 3, kx = tap % 3;
-            // descriptors of the 4 K=16 slices differ only in the start-address field: one 64-bit add each
-            const uint64_t bd0 = umma_desc(sB + bst * C::B_BYTES, C::NLOC * 16, 128);
             const long long t_issue0 = prof_on ? clock64() : 0;
             if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < MT; ++j) {           // every M tile of the unit consumes this weight stage
-                const uint64_t ad0 = umma_desc(sA + ast[j] * TC_A_BYTES + (ky * TC_HW + kx) * 16, TC_A_LBO, TC_A_SBO);
+              for (int kk = 0; kk < C::TPS; ++kk) {
+                const int tap = g * C::TPS + kk;
+                const int ky = tap / 3, kx = tap % 3;
+                // descriptors of the 4 K=16 slices differ only in the start-address field: one 64-bit add each
+                const uint64_t bd0 = umma_desc(sB + bst * C::STAGE_BYTES + kk * C::B_BYTES, C::NLOC * 16, 128);
 #pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  const uint64_t ad = ad0 + (uint64_t)((2 * k16 * TC_A_LBO) >> 4);
-                  const uint64_t bd = bd0 + (uint64_t)((2 * k16 * (C::NLOC * 16)) >> 4);
-                  const uint32_t accum = (c > 0 || ti > 0 || k16 > 0) ? 1u : 0u;
-                  if (CG2) tc_mma2_f16(d_tmem + j * N, ad, bd, idesc, accum);
-                  else tc_mma_f16(d_tmem + j * N, ad, bd, idesc, accum);
+                for (int j = 0; j < MT; ++j) {           // every M tile of the unit consumes this weight stage
+                  const uint64_t ad0 = umma_desc(sA + ast[j] * TC_A_BYTES + (ky * TC_HW + kx) * 16, TC_A_LBO, TC_A_SBO);
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    const uint64_t ad = ad0 + (uint64_t)((2 * k16 * TC_A_LBO) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)((2 * k16 * (C::NLOC * 16)) >> 4);
+                    const uint32_t accum = (c > 0 || ti > 0 || kk > 0 || k16 > 0) ? 1u : 0u;
+                    if (CG2) tc_mma2_f16(d_tmem + j * N, ad, bd, idesc, accum);
+                    else tc_mma_f16(d_tmem + j * N, ad, bd, idesc, accum);
+                  }
                 }
               }
               if (!C::RESIDENT) {            // stage free (in both CTAs) once these MMAs have read it
@@ -421,6 +486,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           else tc_commit(bar_acc_full(as));
         }
         __syncwarp();
+      }
+    } else if (warp == TC_W_MMA && lane == 0) {
+      // CG2 peer: relay the completion of this CTA's A stages to the leader (its bar_b_peer slots double as "peer A full")
+      int aseq = 0;
+      for (int t = 0; t < n_iter; ++t) {
+        for (int c = 0; c < n_src; ++c, ++aseq) {
+          const int st = aseq % C::NA;
+          mbar_wait(bar_a_full(st), (aseq / C::NA) & 1);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_cluster(bar_b_peer(st), 0);
+        }
       }
     }
   } else if (warp < 8) {
@@ -505,14 +581,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
             st_half32(a.net + p * 64 + n0, v);
           }
         } else {  // EPI_DELTA
-          const float* ex = reinterpret_cast<const float*>(smem + C::OFF_EXTRA);
+          // relu(fp16(acc + bias)) stays packed in fp16; the 9-tap dot with the (fp16) delta.2 weights runs on the
+          // mixed-precision FMA (FHFMA: exact fp16 x fp16 product, fp32 accumulate, same channel order as before)
+          const float* exb = reinterpret_cast<const float*>(smem + C::OFF_EXTRA);
+          const __half* exw = reinterpret_cast<const __half*>(smem + C::OFF_EXTRA + 256 * 4);
+          uint32_t hv[16];
+          const __half2 hzero = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaxf(h_round(v[e] + ex[9 * 256 + n0 + e]), 0.f);
+          for (int e2 = 0; e2 < 16; ++e2) {
+            const float2 bb = *reinterpret_cast<const float2*>(exb + n0 + 2 * e2);
+            const __half2 h = __hmax2(__floats2half2_rn(v[2 * e2] + bb.x, v[2 * e2 + 1] + bb.y), hzero);
+            hv[e2] = *reinterpret_cast<const uint32_t*>(&h);
+          }
 #pragma unroll
           for (int q = 0; q < 9; ++q) {
             float acc = t9[q];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) acc = fmaf(v[e], ex[q * 256 + n0 + e], acc);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 w = *reinterpret_cast<const uint4*>(exw + q * 256 + n0 + 8 * j4);
+              acc = fhfma_lo(hv[4 * j4 + 0], w.x, acc); acc = fhfma_hi(hv[4 * j4 + 0], w.x, acc);
+              acc = fhfma_lo(hv[4 * j4 + 1], w.y, acc); acc = fhfma_hi(hv[4 * j4 + 1], w.y, acc);
+              acc = fhfma_lo(hv[4 * j4 + 2], w.z, acc); acc = fhfma_hi(hv[4 * j4 + 2], w.z, acc);
+              acc = fhfma_lo(hv[4 * j4 + 3], w.w, acc); acc = fhfma_hi(hv[4 * j4 + 3], w.w, acc);
+            }
             t9[q] = acc;
           }
         }
@@ -533,6 +624,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
     const int role = warp == 0 ? 0 : warp == TC_W_MMA ? 1 : warp == TC_W_BPROD ? 2 : 3;   // epilogue, mma, b, a
     for (int i = 0; i < 4; ++i) a.prof[role * 8 + i] = (unsigned long long)prof_acc[i];
     a.prof[role * 8 + 7] = (unsigned long long)(clock64() - prof_t0);
+  }
+  if (prof_on && warp == TC_W_DN) {      // dn warp: fill cycles / wait for a free stage, in the A row's spare slots
+    a.prof[3 * 8 + 4] = (unsigned long long)prof_acc[2];
+    a.prof[3 * 8 + 5] = (unsigned long long)prof_acc[0];
   }
   tc_fence_before();
   __syncthreads();

@@ -18,7 +18,8 @@ t = torch.from_numpy
 hp = DepthHotPath(H // 4, W // 4, max_views=V, cascade=[(64, 64, 2), (-1, 320, 2)], use_graph=False)
 hp.load_update_block(sd)
 buf = torch.zeros(4 * 32, dtype=torch.int64, device="cuda")
-_lib.lib().cer_debug_set_conv_profile(buf.data_ptr())
+if not os.environ.get("NO_PROF"):
+    _lib.lib().cer_debug_set_conv_profile(buf.data_ptr())
 args = (t(sc["fmaps"]).cuda().half(), t(sc["net"]).cuda().half(), t(sc["inp"]).cuda().half(),
         t(sc["poses"]).cuda(), t(sc["intrinsics"]).cuda(), 1.0)
 for _ in range(2):
@@ -26,11 +27,11 @@ for _ in range(2):
 torch.cuda.synchronize()
 b = buf.cpu().view(4, 4, 8)
 names = ["corr-enc 3x3 (N=64)", "gates (N=192)", "q/GRU (N=64)", "delta (N=256)"]
-roles = ["epilogue warp0: wait acc_full", "mma: wait acc_empty / a_full / b_full / issue", "B producer: wait b_empty", "A producer: wait a_empty"]
+roles = ["epilogue warp0: wait acc_full", "mma: wait acc_empty / a_full / b_full / issue", "B producer: wait b_empty", "A prod: a_empty / - / - / issue / dn fill / dn wait"]
 print(f"variant {variant}; cycles of CTA 0 (1 cycle ~ 0.52 ns at 1.92 GHz)")
 for k in range(4):
     print(names[k])
     for r in range(4):
         tot = int(b[k, r, 7])
-        w = [int(x) for x in b[k, r, :4]]
+        w = [int(x) for x in b[k, r, :6]]
         print(f"   {roles[r]:42s} total {tot:8d}  waits {w}  ({100 * sum(w[:3]) / max(tot, 1):.0f}% waiting)")
