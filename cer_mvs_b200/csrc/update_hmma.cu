@@ -256,6 +256,208 @@ static size_t lookup_enc1_smem(int D) {
 }
 
 // ------------------------------------------------------------------------------------------
+// KA v2 (plan, D = 64 / 44): the same fused step, restructured around what bounded v1 (ncu: issue slots 37 %, warps
+// stalled on block barriers and on the dependent load -> tap -> MMA phases, 800 instructions per warp):
+//   * warp-autonomous: each warp owns 32 consecutive pixels (8 KB of contiguous volume rows) end to end; the only
+//     block barrier is the one after the constant 1x1 weights, before the dependency wait.  Warps of a CTA and CTAs
+//     of an SM drift into different phases, so row loads of one overlap the tap arithmetic of another.
+//   * every load of the chunk (16 x 16-byte row loads per lane, disparity, origin, 18 delta partials) is issued
+//     before the first use: one latency exposure per chunk instead of three.
+//   * the pyramid is materialised once per chunk in shared memory, zero padded on both sides (levels 1-2 straight
+//     from the row registers), so a tap is two unconditional loads; lane = pixel, odd row pitches.
+//   * the per-tap IEEE division is three FMAs (lookup_tap_padded), bit-identical to v1.
+//   * e1 leaves through a shared-memory transpose: 512-byte contiguous stores instead of 16-byte fragments.
+// ------------------------------------------------------------------------------------------
+constexpr int kL2_WARPS = 4;
+constexpr int kL2_P0 = 67, kL2_P1 = 35, kL2_P2 = 19;        // floats per pixel row incl. the two pads (D <= 64), odd
+constexpr int kL2_WARP_FLOATS = 32 * (kL2_P0 + kL2_P1 + kL2_P2);
+constexpr int kL2_OUT_PITCH = 144;                           // bytes per pixel of the e1 staging tile
+static_assert(32 * kA1Pitch * 2 <= 32 * kL2_P0 * 4, "the A tile aliases the level-0 rows");
+static_assert(32 * kL2_OUT_PITCH <= 32 * (kL2_P1 + kL2_P2) * 4, "the e1 staging tile aliases levels 1-2");
+
+template <int D>
+__global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
+    const float* __restrict__ volume, const float* __restrict__ origin, float* __restrict__ disp,
+    const float* __restrict__ s9, int parts, const float* __restrict__ bd1, int apply_prev, float incre,
+    const __half* __restrict__ w1, const float* __restrict__ b1, __half* __restrict__ e1, int h, int w) {
+  static_assert(D % 4 == 0 && D <= 64 && D >= 8, "row registers / pitches are sized for D <= 64, 16-byte row pieces");
+  constexpr int NV = D / 4;                                  // 16-byte pieces per pixel row = row loads per lane
+  extern __shared__ __align__(16) unsigned char fsm[];
+  __half* sW = reinterpret_cast<__half*>(fsm);                                   // [48][kW1Pitch]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* L0 = reinterpret_cast<float*>(fsm + kCorrK * kW1Pitch * 2) + warp * kL2_WARP_FLOATS;
+  float* L1 = L0 + 32 * kL2_P0;
+  float* L2 = L1 + 32 * kL2_P1;
+  const int px = h * w;
+  const int p0 = (blockIdx.x * kL2_WARPS + warp) * 32;
+  pdl_trigger();
+  for (int i = tid; i < kCorrK * kHid / 8; i += kL2_WARPS * 32) {   // 1x1 weights: constants, before the dependency wait
+    const int k = i / (kHid / 8), c = i % (kHid / 8);
+    *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
+  }
+  __syncthreads();
+  pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
+  if (p0 >= px) return;
+  const int npix = min(32, px - p0);
+  const bool live = lane < npix;
+  const int p = p0 + (live ? lane : 0);
+
+  // ---- issue every load of the chunk ----
+  float4 rv[NV];
+  {
+    const float4* vsrc = reinterpret_cast<const float4*>(volume + (long long)p0 * D);
+    const int nvec = npix * NV;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int f = it * 32 + lane;
+      rv[it] = f < nvec ? __ldg(vsrc + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float dsp = disp[p];
+  const float org = __ldg(origin + p);
+  float sv[9];
+  if (apply_prev) {     // K6 of the previous iteration: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t]))
+    const int x = p % w, y = p / w;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      sv[t] = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
+        sv[t] = (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
+      }
+    }
+  }
+
+  // ---- pyramid rows -> shared memory (pads first: they do not depend on the loads) ----
+  {
+    float* r0 = L0 + lane * kL2_P0;
+    float* r1 = L1 + lane * kL2_P1;
+    float* r2 = L2 + lane * kL2_P2;
+    r0[0] = 0.f; r0[D + 1] = 0.f;
+    r1[0] = 0.f; r1[D / 2 + 1] = 0.f;
+    r2[0] = 0.f; r2[D / 4 + 1] = 0.f;
+  }
+  {
+    // piece f = it * 32 + lane covers elements 4f .. 4f+3 of the chunk; consecutive lanes are 4 words apart, so the four
+    // scalar stores are rotated by lane / 8 (level 1: by lane / 16) to hit 32 distinct banks
+    const int rot = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int f = it * 32 + lane;
+      const int pp = f / NV, i = (f % NV) * 4;               // pixel within the chunk, first element (compile-time NV)
+      const float4 v = rv[it];
+      float* d0 = L0 + pp * kL2_P0 + 1 + i;
+      // rotate (x, y, z, w) left by rot so that component k of the rotated tuple is element (k + rot) & 3
+      const float a0 = (rot & 1) ? v.y : v.x, a1 = (rot & 1) ? v.z : v.y, a2 = (rot & 1) ? v.w : v.z, a3 = (rot & 1) ? v.x : v.w;
+      const float c0 = (rot & 2) ? a2 : a0, c1 = (rot & 2) ? a3 : a1, c2 = (rot & 2) ? a0 : a2, c3 = (rot & 2) ? a1 : a3;
+      d0[(0 + rot) & 3] = c0;
+      d0[(1 + rot) & 3] = c1;
+      d0[(2 + rot) & 3] = c2;
+      d0[(3 + rot) & 3] = c3;
+      const float l1a = (v.x + v.y) * 0.5f, l1b = (v.z + v.w) * 0.5f;     // pyr_value(lvl 1)
+      float* d1 = L1 + pp * kL2_P1 + 1 + i / 2;
+      const int sw = (lane >> 4) & 1;
+      d1[sw] = sw ? l1b : l1a;
+      d1[sw ^ 1] = sw ? l1a : l1b;
+      L2[pp * kL2_P2 + 1 + i / 4] = (l1a + l1b) * 0.5f;                   // pyr_value(lvl 2)
+    }
+  }
+  if (apply_prev) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int x = p % w, y = p / w;
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += sv[t];
+    }
+    dsp += h_round(0.01f * h_round(s + __ldg(bd1)));
+    if (live) disp[p] = dsp;
+  }
+  const float c = live ? lookup_coord(dsp, org, incre, D) : 0.f;
+  __syncwarp();
+
+  // ---- 33 taps of this lane's pixel -> fp16 A row (registers) ----
+  uint32_t arow[kCorrK / 2];
+  {
+    const float* r0 = L0 + lane * kL2_P0 + 1;
+    const float* r1 = L1 + lane * kL2_P1 + 1;
+    const float* r2 = L2 + lane * kL2_P2 + 1;
+    constexpr LevelConst k0 = level_const(D, 0), k1 = level_const(D, 1), k2 = level_const(D, 2);
+    const float c1 = c * 0.5f, c2 = c * 0.25f;
+    float tp[kCorrK];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      tp[j] = lookup_tap_padded(r0, k0, c, j - 5);
+      tp[11 + j] = lookup_tap_padded(r1, k1, c1, j - 5);
+      tp[22 + j] = lookup_tap_padded(r2, k2, c2, j - 5);
+    }
+#pragma unroll
+    for (int k = kCorrPlanes; k < kCorrK; ++k) tp[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCorrK / 2; ++k) {
+      const __half2 hh = __floats2half2_rn(live ? tp[2 * k] : 0.f, live ? tp[2 * k + 1] : 0.f);
+      arow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+  }
+  __syncwarp();                       // every lane is done with the pyramid rows: the A tile may overwrite level 0
+  __half* sA = reinterpret_cast<__half*>(L0);
+#pragma unroll
+  for (int k = 0; k < kCorrK / 8; ++k)
+    *reinterpret_cast<uint4*>(sA + lane * kA1Pitch + k * 8) =
+        make_uint4(arow[4 * k], arow[4 * k + 1], arow[4 * k + 2], arow[4 * k + 3]);
+  __syncwarp();
+
+  // ---- 1x1 conv on mma.sync (two 16-pixel tiles), bias, fp16 rounding, ReLU -> staging tile ----
+  unsigned char* sO = reinterpret_cast<unsigned char*>(L1);
+  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * kW1Pitch + 8 * (lane >> 4)) * 2;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    const uint32_t aBase = smem_u32(sA) + ((mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kA1Pitch + 8 * (lane >> 4)) * 2;
+#pragma unroll
+    for (int k16 = 0; k16 < kCorrK / 16; ++k16) {
+      uint32_t a[4];
+      ldmatrix_x4(a, aBase + k16 * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, bBase + (k16 * 16 * kW1Pitch + j * 16) * 2);
+        mma16816(acc[2 * j], a, b[0], b[1]);
+        mma16816(acc[2 * j + 1], a, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int row = mt * 16 + g + 8 * half;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = j * 8 + q * 2;
+        const float v0 = fmaxf(h_round(acc[j][2 * half] + __ldg(b1 + n)), 0.f);
+        const float v1 = fmaxf(h_round(acc[j][2 * half + 1] + __ldg(b1 + n + 1)), 0.f);
+        *reinterpret_cast<__half2*>(sO + row * kL2_OUT_PITCH + n * 2) = __floats2half2_rn(v0, v1);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- e1: 4 pixels (512 contiguous bytes) per warp store ----
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3), cchunk = lane & 7;
+    if (row < npix)
+      *reinterpret_cast<uint4*>(e1 + (long long)(p0 + row) * 64 + cchunk * 8) =
+          *reinterpret_cast<const uint4*>(sO + row * kL2_OUT_PITCH + cchunk * 16);
+  }
+}
+
+static size_t lookup_enc1_v2_smem() { return (size_t)kCorrK * kW1Pitch * 2 + (size_t)kL2_WARPS * kL2_WARP_FLOATS * 4; }
+
+// ------------------------------------------------------------------------------------------
 // 3x3 implicit-GEMM convolution
 // ------------------------------------------------------------------------------------------
 constexpr int TH = 8, TW = 16;                 // output tile (128 pixels)
@@ -508,6 +710,17 @@ int conv_variant() {
   return g_variant;
 }
 
+// fused lookup kernel of the plan: 2 = warp-autonomous v2 (default), 1 = v1 (CER_LOOKUP=v1 / cer_set_lookup_variant)
+static int g_lookup_variant = -1;
+int lookup_variant() {
+  if (g_lookup_variant < 0) {
+    const char* e = getenv("CER_LOOKUP");
+    g_lookup_variant = (e && !strcmp(e, "v1")) ? 1 : 2;
+  }
+  return g_lookup_variant;
+}
+void set_lookup_variant(int v) { g_lookup_variant = v; }
+
 // Opt in to >48 KB dynamic shared memory once per process (not capturable, so done up front).
 int update_configure() {
   static bool done = false;
@@ -520,6 +733,10 @@ int update_configure() {
   if ((rc = configure_conv<256, EPI_DELTA>())) return rc;
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)lookup_enc1_smem(256)));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_v2_smem()));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v2_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_v2_smem()));
   done = true;
   return CER_OK;
 }
@@ -597,9 +814,22 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
     return CER_ERR_INVALID;
   }
   const bool tc = conv_variant() == 1;
-  CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
-             ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre, (const __half*)(B + L.w1),
-             (const float*)(B + L.b1), ws.e1, h, w);
+  // the two cascade widths of the reference (core/raft.py:77-81) take the warp-autonomous kernel; any other D the general one
+  if (lookup_variant() == 2 && (D == 64 || D == 44)) {
+    const int grid = ceil_div(px, kL2_WARPS * 32);
+    if (D == 64)
+      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v2_kernel<64>, grid, kL2_WARPS * 32, lookup_enc1_v2_smem(), stream, volume, origin,
+                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
+                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
+    else
+      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v2_kernel<44>, grid, kL2_WARPS * 32, lookup_enc1_v2_smem(), stream, volume, origin,
+                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
+                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
+  } else {
+    CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
+               ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre, (const __half*)(B + L.w1),
+               (const float*)(B + L.b1), ws.e1, h, w);
+  }
   if (!tc) CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
   if ((rc = check_launch("lookup_enc1"))) return rc;
   ConvArgs a{};
@@ -744,11 +974,17 @@ int cer_debug_set_conv_profile(void* dev_buf) {
 }
 
 int cer_set_conv_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 4,
+  CER_REQUIRE(variant >= 0 && variant <= 5,
               "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs, 2 tcgen05 one tile per CTA (default), "
-              "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA");
+              "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA, 5 tcgen05 one tile per CTA with 3-tap weight stages");
   g_variant = variant == 0 ? 0 : 1;
-  tc_set_pair_mode(variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : 0);
+  tc_set_pair_mode(variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : variant == 5 ? 4 : 0);
+  return CER_OK;
+}
+
+int cer_set_lookup_variant(int variant) {
+  CER_REQUIRE(variant == 1 || variant == 2, "cer_set_lookup_variant: 1 block-staged kernel, 2 warp-autonomous kernel (default)");
+  set_lookup_variant(variant);
   return CER_OK;
 }
 

@@ -53,7 +53,11 @@ constexpr int TC_DT_H = TC_HH + 6, TC_DT_W = TC_HW + 6;   // disparity tile for 
 // MT2: one CTA owns TWO M = 128 tiles and issues both MMAs against every weight stage, so the weight bytes an SM
 // has to pull through its ~65 GB/s L2 port per output pixel are halved (that port, not the tensor pipe, bounds the
 // streamed-weight convs); the accumulators then fill TMEM (2 x N columns), so the epilogue is not double-buffered.
-enum TcMode { TC_SINGLE = 0, TC_CG2 = 1, TC_MC2 = 2, TC_MT2 = 3 };
+// S3: the 1-CTA form with a whole kernel row (3 taps, 72 KB) per weight stage, two stages: the issuing thread pays one
+// barrier wait + one commit per 12 MMAs (1 150 tensor cycles) instead of per 4 -- its per-step cost (~500 cycles of waits,
+// fences and commits around 384 cycles of MMA work) is what the role profile shows on the gate conv.  N = 192 only
+// (two 3-tap stages of the N = 256 conv do not fit in shared memory).
+enum TcMode { TC_SINGLE = 0, TC_CG2 = 1, TC_MC2 = 2, TC_MT2 = 3, TC_S3 = 4 };
 
 template <int N, int MODE = TC_SINGLE>
 struct TcCfg {
@@ -64,9 +68,11 @@ struct TcCfg {
   // taps per weight stage: the CTA-pair form moves a whole kernel row (3 taps) per stage so that the issuing thread
   // pays one barrier wait + one commit per 12 MMAs instead of per 4 (its per-step cost, not the tensor pipe, bounds
   // the streamed-weight convs); the pair's halved weight footprint is what makes room for it
-  static constexpr int TPS = CG2 ? 3 : 1;
+  static constexpr bool S3 = MODE == TC_S3;
+  static_assert(!S3 || N == 192, "3-tap stages of the 1-CTA form are sized for the gate conv");
+  static constexpr int TPS = (CG2 || S3) ? 3 : 1;
   static constexpr int NG = 9 / TPS;                          // stages per 64-channel chunk
-  static constexpr int NB = RESIDENT ? 9 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
+  static constexpr int NB = RESIDENT ? 9 : S3 ? 2 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
   static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
   // A ring depth (64-channel chunks).  Deeper rings / more accumulator stages for the N = 64 convs were measured
   // slower (q/GRU 36 -> 44 us): those kernels are bound by their per-tile latency chain, not by ring capacity.
@@ -380,16 +386,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
                           ((s + kx) * 2 + (int)rank) * (C::B_BYTES / 256), bar_b_full(st));
               continue;
             }
-            mbar_expect_tx(bar_b_full(st), C::B_BYTES);
+            mbar_expect_tx(bar_b_full(st), MC2 ? C::B_BYTES : C::STAGE_BYTES);
             if (MC2) {
               // my half of the tile goes to both CTAs (same offset), the peer sends the other half
               constexpr uint32_t HALF = C::B_BYTES / 2;
               bulk_g2s_mc(sB + st * C::STAGE_BYTES + rank * HALF, wsrc + (size_t)s * C::B_BYTES + rank * HALF, HALF,
                           bar_b_full(st), (uint16_t)3);
             } else {
-              // CG2: this CTA's half of the output channels is one contiguous slice of the pair layout
-              bulk_g2s(sB + st * C::STAGE_BYTES, wsrc + ((size_t)s * (CG2 ? 2 : 1) + rank) * C::B_BYTES, C::B_BYTES,
-                       bar_b_full(st));
+              // one copy per stage: the TPS taps of a kernel row are adjacent tiles of the packed weights
+              bulk_g2s(sB + st * C::STAGE_BYTES, wsrc + (size_t)s * C::B_BYTES, C::STAGE_BYTES, bar_b_full(st));
             }
           }
         }
@@ -659,6 +664,9 @@ static int tc_configure_one() {
     constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
     CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TcCfg<N, M3>::TOTAL));
+    constexpr int M4 = N == 192 ? TC_S3 : TC_SINGLE;
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<N, M4>::TOTAL));
   }
   return CER_OK;
 }
@@ -754,7 +762,15 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
     CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, TC_THREADS, (TcCfg<N, M3>::TOTAL), stream, a, nomap);
     return check_launch("conv3x3_tc");
   }
-  if (N != 64 && tiles >= 2 && g_pair_mode != TC_SINGLE) {
+  if (N == 192 && g_pair_mode == TC_S3) {
+    constexpr int M4 = N == 192 ? TC_S3 : TC_SINGLE;
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    CUtensorMap nomap;
+    memset(&nomap, 0, sizeof(nomap));
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M4>), grid, TC_THREADS, (TcCfg<N, M4>::TOTAL), stream, a, nomap);
+    return check_launch("conv3x3_tc");
+  }
+  if (N != 64 && tiles >= 2 && g_pair_mode != TC_SINGLE && g_pair_mode != TC_S3) {
     constexpr int M1 = N != 64 ? TC_CG2 : TC_SINGLE, M2 = N != 64 ? TC_MC2 : TC_SINGLE;
     return g_pair_mode == TC_CG2 ? launch_pair<N, EPI, M1>(a, tiles, kind, stream)
                                  : launch_pair<N, EPI, M2>(a, tiles, kind, stream);

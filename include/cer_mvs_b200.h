@@ -132,6 +132,10 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
  * Takes effect for launches and graph captures issued afterwards. */
 int cer_set_conv_variant(int variant);
 
+/* Which fused lookup + 1x1-encoder kernel the plan uses (A/B switch): 2 = warp-autonomous kernel for the two cascade
+ * widths D = 64 / 44 (default), 1 = the block-staged kernel (any D <= 256; CER_LOOKUP=v1).  Results are bit-identical. */
+int cer_set_lookup_variant(int variant);
+
 /* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */
 int cer_debug_set_conv_profile(void* dev_buf);
 

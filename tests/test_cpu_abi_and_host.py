@@ -143,3 +143,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "cer_oracle" not in text and "import oracle" not in text, f
+
+
+def test_three_fma_division_is_correctly_rounded():
+    """lookup_common.cuh divides by (W_l - 1) as q0 = x*rcp, r = fma(-q0, d, x), q = fma(r, rcp, q0) with
+    rcp = RN(1/d).  Emulate the fp32 FMAs in float64 (all products are exact there) and compare with IEEE fp32
+    division for every divisor the kernels can meet (W_l - 1 for D <= 256) over lookup-coordinate-like inputs."""
+    rng = np.random.default_rng(0)
+    n = 200_000
+    xs = np.concatenate([rng.uniform(-6, 70, n), rng.uniform(-6, 6, n), rng.standard_normal(n) * 1e-3,
+                         rng.uniform(0, 1e6, n), np.ldexp(rng.uniform(1, 2, n), rng.integers(-20, 60, n))]).astype(np.float32)
+    for d in range(1, 256):
+        d32 = np.float32(d)
+        rcp = np.float32(1.0) / d32
+        q0 = (xs * rcp).astype(np.float32)
+        r = xs.astype(np.float64) - q0.astype(np.float64) * float(d32)
+        r32 = r.astype(np.float32)
+        assert np.array_equal(r32.astype(np.float64), r)          # the residual is exactly representable
+        q = (q0.astype(np.float64) + r32.astype(np.float64) * float(rcp)).astype(np.float32)
+        assert np.array_equal(q, (xs / d32).astype(np.float32)), d
