@@ -304,6 +304,43 @@ def run_ours(args):
             "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["ms_per_step"] /
             sum(v["ms_per_step"] for v in kernels.values())}
 
+    # ---- the stand-alone correlation-lookup kernel (CorrBlock.__call__ drop-in, cer_lookup) on per-view volumes:
+    # slots = V, so one launch moves V * px * (4 D + 8 + 132) bytes (303 MB of volume: larger than L2, nothing is
+    # reused between launches); algorithmic bytes per SURVEY 8d = slots * px * 284 ----
+    lookup_roof = None
+    if rank == 0:
+        L = _lib.lib()
+        Dl, incre = 64, 0.0025 / 64
+        g = torch.Generator(device=dev).manual_seed(1)
+        vol = torch.randn(V, px, Dl, device=dev, generator=g)
+        origin = torch.full((px,), 32 * incre, device=dev)
+        zinv = origin + (torch.rand(px, device=dev, generator=g) * 40 - 20) * incre
+        lout = torch.empty(V, 33, px, device=dev)
+        st = _lib.stream_ptr()
+
+        def run_lookup():
+            _lib.check(L.cer_lookup(vol.data_ptr(), V, origin.data_ptr(), zinv.data_ptr(), Dl, incre, 5, 3,
+                                    lout.data_ptr(), h1, w1, st), "cer_lookup")
+        for _ in range(3):
+            run_lookup()
+        torch.cuda.synchronize()
+        n_l = 20
+        e0.record()
+        for _ in range(n_l):
+            run_lookup()
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / n_l
+        alg_b, moved_b = V * px * 284.0, V * px * (4.0 * Dl + 8 + 132)
+        lookup_roof = {"kernel": "lookup_v2_kernel<64> (cer_lookup, slots = V per-view volumes)", "bound": "hbm",
+                       "achieved": alg_b / (us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                       "frac": alg_b / (us * 1e-6) / 1e9 / pk["hbm"], "avg_launch_us": us,
+                       "design_bytes_per_launch": moved_b, "design_gbs": moved_b / (us * 1e-6) / 1e9,
+                       "design_frac": moved_b / (us * 1e-6) / 1e9 / pk["hbm"],
+                       "note": "rows are read whole (4D+8 B in, 132 B out per pixel-slot = 396 B at D=64), so 284 "
+                               "algorithmic bytes cap 'frac' at 0.72 of the achieved HBM fraction ('design_frac')"}
+        del vol, lout
+
     # ---- view-sharded single image (NCCL all-reduce of the partial volume per stage) ----
     viewshard = None
     if world > 1 and world <= V:
@@ -340,7 +377,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "sync_call_ms": sync_ms,
                     "api": "cer_plan_submit_host / cer_plan_wait_host (pinned host buffers, 2 jobs in flight)"},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": kernels,
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "lookup_roofline": lookup_roof,
+            "cpu_baseline": cpu, "kernels": kernels,
         }
         if viewshard:
             line["viewshard"] = viewshard

@@ -249,7 +249,11 @@ __global__ void __launch_bounds__(256) build_volume_h16_kernel(
     int h, int w) {
   __shared__ float sP[kMaxPairs][12];
   __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
-  __shared__ __align__(16) int sS[64 * 4 * 8];   // per 4-lane group: 4 samples x {4 byte offsets, 4 weights}
+  // per 4-lane group: 4 samples x {4 byte offsets, 4 weights} = 32 words, padded to 36: a quarter-warp (two groups)
+  // then reads / writes its two 16-byte slots in different banks (ncu: every LDS.128 / STS.128 of the unpadded layout
+  // took 8 wavefronts instead of 4, a third of this L1-bound kernel's wavefronts)
+  constexpr int kGrpWords = 36;
+  __shared__ __align__(16) int sS[64 * kGrpWords];
   for (int t = threadIdx.x; t < n_pairs * 12; t += blockDim.x) sP[t / 12][t % 12] = Pij[(t / 12) * 16 + (t % 12)];
   for (int t = threadIdx.x; t < n_pairs; t += blockDim.x) {
     sI[t] = ii[t];
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(256) build_volume_h16_kernel(
   const long long img_stride = px * kFeatC;
   int cached_ref = -1;
   Slice16 f1;
-  int* grp = sS + (threadIdx.x >> 2) * 32;
+  int* grp = sS + (threadIdx.x >> 2) * kGrpWords;
 
   const int chunk0 = blockIdx.y * kH16Chunks;
   for (int ch = chunk0; ch < chunk0 + kH16Chunks; ++ch) {

@@ -280,6 +280,46 @@ __global__ void __launch_bounds__(kLookupPix) lookup_kernel(
       o_ptr[(long long)(lvl * taps + (j + radius)) * px] = lookup_tap(row, D, lvl, j, c);
 }
 
+// ------------------------------------------------------------------------------------------
+// The reference configuration (radius 5, 3 levels, D = 64 / 44: core/raft.py:77-81) takes a warp-autonomous kernel:
+// a warp owns 32 consecutive pixels of one slot, brings their 32 * D contiguous floats in with 16-byte loads that
+// are all in flight at once, materialises the zero-padded three-level pyramid in its own shared-memory slice
+// (no block barrier anywhere), then lane = pixel evaluates the 33 taps and every tap leaves as one coalesced
+// 128-byte store.  HBM traffic per (pixel, slot): 4 * D + 8 in, 132 out (SURVEY 8d counts 284 B algorithmic).
+// ------------------------------------------------------------------------------------------
+constexpr int kLookupV2Warps = 4;
+
+template <int D>
+__global__ void __launch_bounds__(kLookupV2Warps * 32, 3) lookup_v2_kernel(
+    const float* __restrict__ volume, const float* __restrict__ origin, const float* __restrict__ zinv,
+    long long zinv_stride, float incre, float* __restrict__ out, int px) {
+  extern __shared__ __align__(16) float pyr[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* L0 = pyr + warp * kPyrWarpFloats;
+  float* L1 = L0 + 32 * kPyrP0;
+  float* L2 = L1 + 32 * kPyrP1;
+  const int slot = blockIdx.y;
+  const int p0 = (blockIdx.x * kLookupV2Warps + warp) * 32;
+  if (p0 >= px) return;
+  const int npix = min(32, px - p0);
+  const bool live = lane < npix;
+  const int p = p0 + (live ? lane : 0);
+  float4 rv[D / 4];
+  pyr_load_chunk<D>(volume + ((long long)slot * px + p0) * D, npix, lane, rv);
+  const float z = __ldg(zinv + slot * zinv_stride + p);
+  const float o = __ldg(origin + p);
+  pyr_store_chunk<D>(rv, L0, L1, L2, lane);
+  const float c = lookup_coord(z, o, incre, D);
+  __syncwarp();
+  float tp[33];
+  pyr_taps33<D>(L0, L1, L2, lane, c, tp);
+  if (live) {
+    float* o_ptr = out + (long long)slot * 33 * px + p;
+#pragma unroll
+    for (int k = 0; k < 33; ++k) __stcs(o_ptr + (long long)k * px, tp[k]);      // streamed: written once, read by the encoder
+  }
+}
+
 }  // namespace cer
 
 using namespace cer;
@@ -387,6 +427,23 @@ int cer_lookup_strided(const float* volume, int slots, const float* origin, cons
   CER_REQUIRE((D >> (num_levels - 1)) >= 2, "cer_lookup: D too small for %d levels", num_levels);
   CER_REQUIRE(D <= 1024, "cer_lookup: D > 1024 unsupported");
   const long long px = (long long)h * w;
+  if (lookup_variant() == 2 && radius == 5 && num_levels == 3 && (D == 64 || D == 44) && px < (1ll << 31) - 64) {
+    static bool configured = false;
+    const size_t smem2 = (size_t)kLookupV2Warps * kPyrWarpFloats * sizeof(float);
+    if (!configured) {
+      CER_CUDA(cudaFuncSetAttribute(lookup_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      CER_CUDA(cudaFuncSetAttribute(lookup_v2_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured = true;
+    }
+    dim3 grid2(ceil_div(px, kLookupV2Warps * 32), slots);
+    if (D == 64)
+      CER_LAUNCH(KK_LOOKUP, lookup_v2_kernel<64>, grid2, kLookupV2Warps * 32, smem2, stream, volume, origin, zinv, zinv_stride,
+                 incre, out, (int)px);
+    else
+      CER_LAUNCH(KK_LOOKUP, lookup_v2_kernel<44>, grid2, kLookupV2Warps * 32, smem2, stream, volume, origin, zinv, zinv_stride,
+                 incre, out, (int)px);
+    return check_launch("cer_lookup");
+  }
   const size_t smem = (size_t)kLookupPix * (D + 1) * sizeof(float);
   if (smem > 48 * 1024)
     CER_CUDA(cudaFuncSetAttribute(lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -269,8 +269,8 @@ static size_t lookup_enc1_smem(int D) {
 //   * e1 leaves through a shared-memory transpose: 512-byte contiguous stores instead of 16-byte fragments.
 // ------------------------------------------------------------------------------------------
 constexpr int kL2_WARPS = 4;
-constexpr int kL2_P0 = 67, kL2_P1 = 35, kL2_P2 = 19;        // floats per pixel row incl. the two pads (D <= 64), odd
-constexpr int kL2_WARP_FLOATS = 32 * (kL2_P0 + kL2_P1 + kL2_P2);
+constexpr int kL2_P0 = kPyrP0, kL2_P1 = kPyrP1, kL2_P2 = kPyrP2;      // padded level rows (lookup_common.cuh)
+constexpr int kL2_WARP_FLOATS = kPyrWarpFloats;
 constexpr int kL2_OUT_PITCH = 144;                           // bytes per pixel of the e1 staging tile
 static_assert(32 * kA1Pitch * 2 <= 32 * kL2_P0 * 4, "the A tile aliases the level-0 rows");
 static_assert(32 * kL2_OUT_PITCH <= 32 * (kL2_P1 + kL2_P2) * 4, "the e1 staging tile aliases levels 1-2");
@@ -289,30 +289,27 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
   float* L1 = L0 + 32 * kL2_P0;
   float* L2 = L1 + 32 * kL2_P1;
   const int px = h * w;
-  const int p0 = (blockIdx.x * kL2_WARPS + warp) * 32;
+  // a warp past the end of the image (last CTA only) runs on pixel 0 with npix = 0: every store is guarded by npix, and
+  // the CTA keeps one barrier for all warps
+  const int p0_raw = (blockIdx.x * kL2_WARPS + warp) * 32;
+  const int p0 = p0_raw < px ? p0_raw : 0;
   pdl_trigger();
-  for (int i = tid; i < kCorrK * kHid / 8; i += kL2_WARPS * 32) {   // 1x1 weights: constants, before the dependency wait
-    const int k = i / (kHid / 8), c = i % (kHid / 8);
-    *reinterpret_cast<uint4*>(sW + k * kW1Pitch + c * 8) = __ldg(reinterpret_cast<const uint4*>(w1 + k * kHid) + c);
-  }
-  __syncthreads();
+  // 1x1 weights: constants, requested before the dependency wait; they are parked in registers until the chunk's own
+  // loads are in flight too, so a CTA pays ONE global-latency exposure, not two (ncu: 20 % of the v2 kernel's stall
+  // samples sat on the weight store that used to come first)
+  constexpr int WQ = kCorrK * kHid / 8 / (kL2_WARPS * 32);
+  static_assert(WQ * kL2_WARPS * 32 * 8 == kCorrK * kHid, "weight pieces divide evenly over the CTA");
+  uint4 wreg[WQ];
+#pragma unroll
+  for (int q = 0; q < WQ; ++q) wreg[q] = __ldg(reinterpret_cast<const uint4*>(w1) + q * kL2_WARPS * 32 + tid);
   pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
-  if (p0 >= px) return;
-  const int npix = min(32, px - p0);
+  const int npix = p0_raw < px ? min(32, px - p0) : 0;
   const bool live = lane < npix;
   const int p = p0 + (live ? lane : 0);
 
   // ---- issue every load of the chunk ----
   float4 rv[NV];
-  {
-    const float4* vsrc = reinterpret_cast<const float4*>(volume + (long long)p0 * D);
-    const int nvec = npix * NV;
-#pragma unroll
-    for (int it = 0; it < NV; ++it) {
-      const int f = it * 32 + lane;
-      rv[it] = f < nvec ? __ldg(vsrc + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
+  pyr_load_chunk<D>(volume + (long long)p0 * D, npix, lane, rv);
   float dsp = disp[p];
   const float org = __ldg(origin + p);
   float sv[9];
@@ -329,40 +326,13 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
     }
   }
 
-  // ---- pyramid rows -> shared memory (pads first: they do not depend on the loads) ----
-  {
-    float* r0 = L0 + lane * kL2_P0;
-    float* r1 = L1 + lane * kL2_P1;
-    float* r2 = L2 + lane * kL2_P2;
-    r0[0] = 0.f; r0[D + 1] = 0.f;
-    r1[0] = 0.f; r1[D / 2 + 1] = 0.f;
-    r2[0] = 0.f; r2[D / 4 + 1] = 0.f;
-  }
-  {
-    // piece f = it * 32 + lane covers elements 4f .. 4f+3 of the chunk; consecutive lanes are 4 words apart, so the four
-    // scalar stores are rotated by lane / 8 (level 1: by lane / 16) to hit 32 distinct banks
-    const int rot = lane >> 3;
 #pragma unroll
-    for (int it = 0; it < NV; ++it) {
-      const int f = it * 32 + lane;
-      const int pp = f / NV, i = (f % NV) * 4;               // pixel within the chunk, first element (compile-time NV)
-      const float4 v = rv[it];
-      float* d0 = L0 + pp * kL2_P0 + 1 + i;
-      // rotate (x, y, z, w) left by rot so that component k of the rotated tuple is element (k + rot) & 3
-      const float a0 = (rot & 1) ? v.y : v.x, a1 = (rot & 1) ? v.z : v.y, a2 = (rot & 1) ? v.w : v.z, a3 = (rot & 1) ? v.x : v.w;
-      const float c0 = (rot & 2) ? a2 : a0, c1 = (rot & 2) ? a3 : a1, c2 = (rot & 2) ? a0 : a2, c3 = (rot & 2) ? a1 : a3;
-      d0[(0 + rot) & 3] = c0;
-      d0[(1 + rot) & 3] = c1;
-      d0[(2 + rot) & 3] = c2;
-      d0[(3 + rot) & 3] = c3;
-      const float l1a = (v.x + v.y) * 0.5f, l1b = (v.z + v.w) * 0.5f;     // pyr_value(lvl 1)
-      float* d1 = L1 + pp * kL2_P1 + 1 + i / 2;
-      const int sw = (lane >> 4) & 1;
-      d1[sw] = sw ? l1b : l1a;
-      d1[sw ^ 1] = sw ? l1a : l1b;
-      L2[pp * kL2_P2 + 1 + i / 4] = (l1a + l1b) * 0.5f;                   // pyr_value(lvl 2)
-    }
+  for (int q = 0; q < WQ; ++q) {
+    const int i = q * kL2_WARPS * 32 + tid;
+    *reinterpret_cast<uint4*>(sW + (i / (kHid / 8)) * kW1Pitch + (i % (kHid / 8)) * 8) = wreg[q];
   }
+  // ---- pyramid rows -> shared memory ----
+  pyr_store_chunk<D>(rv, L0, L1, L2, lane);
   if (apply_prev) {
     float s = 0.f;
 #pragma unroll
@@ -380,18 +350,10 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
   // ---- 33 taps of this lane's pixel -> fp16 A row (registers) ----
   uint32_t arow[kCorrK / 2];
   {
-    const float* r0 = L0 + lane * kL2_P0 + 1;
-    const float* r1 = L1 + lane * kL2_P1 + 1;
-    const float* r2 = L2 + lane * kL2_P2 + 1;
-    constexpr LevelConst k0 = level_const(D, 0), k1 = level_const(D, 1), k2 = level_const(D, 2);
-    const float c1 = c * 0.5f, c2 = c * 0.25f;
-    float tp[kCorrK];
+    float tp33[33], tp[kCorrK];
+    pyr_taps33<D>(L0, L1, L2, lane, c, tp33);
 #pragma unroll
-    for (int j = 0; j < 11; ++j) {
-      tp[j] = lookup_tap_padded(r0, k0, c, j - 5);
-      tp[11 + j] = lookup_tap_padded(r1, k1, c1, j - 5);
-      tp[22 + j] = lookup_tap_padded(r2, k2, c2, j - 5);
-    }
+    for (int k = 0; k < kCorrPlanes; ++k) tp[k] = tp33[k];
 #pragma unroll
     for (int k = kCorrPlanes; k < kCorrK; ++k) tp[k] = 0.f;
 #pragma unroll
@@ -406,7 +368,7 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
   for (int k = 0; k < kCorrK / 8; ++k)
     *reinterpret_cast<uint4*>(sA + lane * kA1Pitch + k * 8) =
         make_uint4(arow[4 * k], arow[4 * k + 1], arow[4 * k + 2], arow[4 * k + 3]);
-  __syncwarp();
+  __syncthreads();                    // the only CTA barrier: the 1x1 weights of all four warps are in place (and my A tile)
 
   // ---- 1x1 conv on mma.sync (two 16-pixel tiles), bias, fp16 rounding, ReLU -> staging tile ----
   unsigned char* sO = reinterpret_cast<unsigned char*>(L1);
@@ -698,14 +660,14 @@ static int configure_conv() {
   return CER_OK;
 }
 
-void tc_set_pair_mode(int mode);   // 0 single CTA, 1 cta_group::2 pairs, 2 multicast pairs
+void tc_set_pair_mode(int gates_mode, int delta_mode);   // 0 single CTA, 1 cta_group::2 pairs, 2 multicast pairs, 3 two tiles, 4 3-tap stages
 static int g_variant = -1;
 int conv_variant() {
   if (g_variant < 0) {
     const char* e = getenv("CER_CONV");
     g_variant = (e && !strcmp(e, "hmma")) ? 0 : 1;
-    if (e && !strcmp(e, "tc2")) tc_set_pair_mode(1);
-    if (e && !strcmp(e, "tc1")) tc_set_pair_mode(0);
+    if (e && !strcmp(e, "tc2")) tc_set_pair_mode(1, 1);
+    if (e && !strcmp(e, "tc1")) tc_set_pair_mode(0, 0);
   }
   return g_variant;
 }
@@ -974,11 +936,13 @@ int cer_debug_set_conv_profile(void* dev_buf) {
 }
 
 int cer_set_conv_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 5,
-              "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs, 2 tcgen05 one tile per CTA (default), "
-              "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA, 5 tcgen05 one tile per CTA with 3-tap weight stages");
+  CER_REQUIRE(variant >= 0 && variant <= 6,
+              "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs, 2 tcgen05 one tile per CTA, "
+              "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA, 5 tcgen05 one tile per CTA with 3-tap weight stages, "
+              "6 cta_group::2 pairs for the gate conv + one tile per CTA for the delta conv (default)");
   g_variant = variant == 0 ? 0 : 1;
-  tc_set_pair_mode(variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : variant == 5 ? 4 : 0);
+  const int m = variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : variant == 5 ? 4 : 0;
+  tc_set_pair_mode(variant == 6 ? 1 : m, variant == 5 || variant == 6 ? 0 : m);
   return CER_OK;
 }
 

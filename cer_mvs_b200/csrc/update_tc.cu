@@ -522,6 +522,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
       // operands of the element-wise GRU algebra do not depend on the accumulator: fetch them before waiting for it
       uint4 pre_a[4];
       if (EPI == EPI_GATES && ok) ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);   // net slice of this thread's r chunk
+      uint4 pre_z[4];
+      float4 pre_q[8];
+      if (EPI == EPI_GRUOUT && ok) {          // z, net and the x-part of q for this thread's 32 channels (N = 64: cb == chalf)
+        ldg_half32_raw(a.z + p * 64 + chalf * 32, pre_z);
+        ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);
+        const float4* q = reinterpret_cast<const float4*>(a.qx + p * 64 + chalf * 32);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pre_q[e] = q[e];
+      }
       if (j == 0) pwait(bar_acc_full(as), (t / C::NACC) & 1, 0);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * N) + j * N;
@@ -569,19 +578,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           }
         } else if (EPI == EPI_GRUOUT) {
           if (ok) {
-            float zz[32], nt[32];
-            ld_half32(a.z + p * 64 + n0, zz);
-            ld_half32(a.net + p * 64 + n0, nt);
-            const float4* q = reinterpret_cast<const float4*>(a.qx + p * 64 + n0);
+            // 8 channels at a time straight from the packed prefetch registers (keeps the live set under 128 registers)
+            const uint32_t* zp = reinterpret_cast<const uint32_t*>(pre_z);
+            const uint32_t* np_ = reinterpret_cast<const uint32_t*>(pre_a);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 qq = q[e];
-              v[4 * e] += qq.x; v[4 * e + 1] += qq.y; v[4 * e + 2] += qq.z; v[4 * e + 3] += qq.w;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float qv = h_round(fast_tanh(h_round(v[e])));
-              v[e] = h_round(h_round(h_round(1.f - zz[e]) * nt[e]) + h_round(zz[e] * qv));
+            for (int e2 = 0; e2 < 16; ++e2) {
+              const float2 zz = __half22float2(*reinterpret_cast<const __half2*>(&zp[e2]));
+              const float2 nt = __half22float2(*reinterpret_cast<const __half2*>(&np_[e2]));
+              const float4 qq = pre_q[e2 >> 1];
+              const float qa = (e2 & 1) ? qq.z : qq.x, qb = (e2 & 1) ? qq.w : qq.y;
+              const float q0 = h_round(fast_tanh(h_round(v[2 * e2] + qa)));
+              const float q1 = h_round(fast_tanh(h_round(v[2 * e2 + 1] + qb)));
+              v[2 * e2] = h_round(h_round(h_round(1.f - zz.x) * nt.x) + h_round(zz.x * q0));
+              v[2 * e2 + 1] = h_round(h_round(h_round(1.f - zz.y) * nt.y) + h_round(zz.y * q1));
             }
             st_half32(a.net + p * 64 + n0, v);
           }
@@ -649,7 +658,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
 
 // ---- host ----------------------------------------------------------------------------------------
 // Pair modes apply to the N = 192 / 256 convs (weights streamed per tile); the N = 64 convs keep their weights resident.
-static int g_pair_mode = TC_SINGLE;   // TC_SINGLE / TC_CG2 / TC_MC2 / TC_MT2 for the streamed-weight convs (A/B switch)
+// Mode of the streamed-weight convs (A/B switch), per kernel: [0] gate conv (N = 192), [1] delta conv (N = 256).
+// Measured default: CTA pairs for the gate conv (90 vs 101 us), single CTAs for the delta conv (51 vs 52 us).
+static int g_pair_modes[2] = {TC_CG2, TC_SINGLE};
 
 template <int N, int EPI>
 static int tc_configure_one() {
@@ -680,7 +691,10 @@ int tc_configure() {
   return CER_OK;
 }
 
-void tc_set_pair_mode(int mode) { g_pair_mode = mode; }
+void tc_set_pair_mode(int gates_mode, int delta_mode) {
+  g_pair_modes[0] = gates_mode;
+  g_pair_modes[1] = delta_mode;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -753,6 +767,7 @@ template <int N, int EPI>
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = ((a.w + TC_TW - 1) / TC_TW) * ((a.h + TC_TH - 1) / TC_TH);
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
+  const int g_pair_mode = N == 192 ? g_pair_modes[0] : N == 256 ? g_pair_modes[1] : TC_SINGLE;
   if (N != 64 && tiles >= 2 && g_pair_mode == TC_MT2) {
     constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
     const int units = (tiles + 1) / 2;

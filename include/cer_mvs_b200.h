@@ -123,11 +123,13 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     cer_stream_t stream);
 
 /* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on all of them):
- *   2 = tcgen05.mma + TMEM, persistent CTAs, one 128-pixel tile per CTA at a time (default; CER_CONV unset)
- *   1 = the N >= 192 convolutions as CTA pairs issuing cta_group::2 MMAs (M = 256), weights by TMA tensor loads that
- *       credit the leader's barrier (CER_CONV=tc2)
+ *   6 = default (CER_CONV unset): tcgen05.mma + TMEM, persistent CTAs; the gate conv (N = 192) as CTA pairs issuing
+ *       cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), every other conv one 128-pixel tile per CTA
+ *   2 = every conv one 128-pixel tile per CTA at a time (CER_CONV=tc1)
+ *   1 = both N >= 192 convolutions as cta_group::2 CTA pairs (CER_CONV=tc2)
  *   3 = the N >= 192 convolutions as 2-CTA clusters that multicast each weight tile
  *   4 = the N >= 192 convolutions with two 128-pixel tiles per CTA sharing each weight stage
+ *   5 = the gate conv with a whole kernel row (3 taps) per weight stage, one tile per CTA
  *   0 = mma.sync (the v1 kernels; CER_CONV=hmma).
  * Takes effect for launches and graph captures issued afterwards. */
 int cer_set_conv_variant(int variant);

@@ -117,6 +117,25 @@ def test_lookup(golden, stage, per_view):
         np.testing.assert_allclose(out, want, rtol=1e-5, atol=3e-6)
 
 
+@pytest.mark.parametrize("stage", [0, 1])
+def test_lookup_variants_bit_identical(golden, stage, build_variant):
+    """Warp-autonomous lookup kernel (reference configuration, default) == general kernel, bit for bit, on a ragged
+    pixel count (560 = 17.5 warps) and on lookups that leave the volume on both sides."""
+    if build_variant != "fhfma":
+        pytest.skip("independent of the build kernel")
+    from cer_mvs_b200 import _lib
+    cb, g = _block(golden, stage, per_view=True)
+    outs = {}
+    try:
+        for v in (1, 2):
+            _lib.check(_lib.lib().cer_set_lookup_variant(v))
+            outs[v] = [cb(t(g[f"s{stage}_z_{name}"]).cuda()[:, [0] * V]).cpu().numpy() for name in ("true", "zero", "far", "rand")]
+    finally:
+        _lib.lib().cer_set_lookup_variant(2)
+    for a, b in zip(outs[1], outs[2]):
+        assert np.array_equal(a, b)
+
+
 def test_identity_view_known_answer():
     """Source view == reference view with the same pose: every hypothesis reprojects onto the pixel
     itself, so the volume is |f|^2/64 for every d (size-independent known answer)."""
