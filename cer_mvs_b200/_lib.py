@@ -33,6 +33,10 @@ SIGNATURES = {
                            c_int, c_void_p]),
     "cer_lookup_strided": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p,
                                    c_int, c_int, c_void_p]),
+    "cer_normalize_images": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "cer_resize_bilinear_ac": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "cer_disp_to_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cer_multires_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "cer_set_conv_variant": (c_int, [c_int]),
     "cer_set_lookup_variant": (c_int, [c_int]),
     "cer_debug_set_conv_profile": (c_int, [c_void_p]),

@@ -1,0 +1,130 @@
+"""Image preparation, depth output and the multi-resolution merge around the hot path,
+under the reference's own function names so that ``inference.py`` / ``multires.py`` can call them unchanged:
+
+* ``scale_operation`` / ``crop_operation``  (utils/data_utils.py:58-79)
+* ``normalize_images``                       (core/raft.py:40-41, ``images *= 2 / 255.; images -= 1``)
+* ``disp_to_depth``                          (inference.py:57-58, ``np.where(res == 0, 0, 1 / res)``)
+* ``write_pfm`` / ``readPFM``                (utils/frame_utils.py:138-164, 10-40)
+* ``multires_merge``                         (multires.py:24-28)
+
+The array work runs in csrc/io_ops.cu on CUDA tensors; there is no CPU fallback (CPU tensors raise).  PFM
+reading/writing is host file I/O by nature; the writer takes the depth map already flipped by the kernel.
+"""
+import re
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _need_cuda_f32(x, name):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32")
+    return x.contiguous()
+
+
+def scale_operation(images, intrinsics, s):
+    """images [N,3,H,W] float32 cuda, intrinsics [N,3,3] (modified in place like the reference's) -> rescaled pair."""
+    images = _need_cuda_f32(images, "images")
+    n, c, ht1, wd1 = images.shape
+    ht2, wd2 = int(s * ht1), int(s * wd1)
+    intrinsics[:, 0] *= s
+    intrinsics[:, 1] *= s
+    out = torch.empty(n, c, ht2, wd2, device=images.device, dtype=torch.float32)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.lib().cer_resize_bilinear_ac(images.data_ptr(), out.data_ptr(), n * c, ht1, wd1, ht2, wd2,
+                                                     _lib.stream_ptr()), "cer_resize_bilinear_ac")
+    return out, intrinsics
+
+
+def crop_operation(images, intrinsics, crop_h, crop_w):
+    """Centre crop; a view plus an intrinsics shift (no kernel: the next stage reads the strided view once)."""
+    ht1, wd1 = images.shape[2], images.shape[3]
+    x0, y0 = (wd1 - crop_w) // 2, (ht1 - crop_h) // 2
+    images = images[:, :, y0:y0 + crop_h, x0:x0 + crop_w]
+    intrinsics[:, 0, 2] -= x0
+    intrinsics[:, 1, 2] -= y0
+    return images, intrinsics
+
+
+def normalize_images(images, out=None):
+    images = _need_cuda_f32(images, "images")
+    out = torch.empty_like(images) if out is None else out
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.lib().cer_normalize_images(images.data_ptr(), out.data_ptr(), images.numel(),
+                                                   _lib.stream_ptr()), "cer_normalize_images")
+    return out
+
+
+def disp_to_depth(disp, flip_rows=False):
+    """disp [..., h, w] float32 cuda -> depth of the same shape (rows bottom-up if flip_rows, as PFM stores them)."""
+    disp = _need_cuda_f32(disp, "disp")
+    h, w = disp.shape[-2:]
+    if disp.numel() != h * w:
+        raise RuntimeError("disp_to_depth: one map at a time")
+    out = torch.empty_like(disp)
+    with torch.cuda.device(disp.device):
+        _lib.check(_lib.lib().cer_disp_to_depth(disp.data_ptr(), out.data_ptr(), h, w, int(flip_rows),
+                                                _lib.stream_ptr()), "cer_disp_to_depth")
+    return out
+
+
+def multires_merge(im1, im2, th=0.02):
+    """im1 [h1,w1] (scale-1 depth), im2 [h2,w2] (scale-2 depth), float32 cuda -> merged [h2,w2]."""
+    im1, im2 = _need_cuda_f32(im1, "im1"), _need_cuda_f32(im2, "im2")
+    out = torch.empty_like(im2)
+    with torch.cuda.device(im2.device):
+        _lib.check(_lib.lib().cer_multires_merge(im1.data_ptr(), im1.shape[0], im1.shape[1], im2.data_ptr(),
+                                                 im2.shape[0], im2.shape[1], float(th), out.data_ptr(),
+                                                 _lib.stream_ptr()), "cer_multires_merge")
+    return out
+
+
+def write_pfm(file, image, scale=1, flipped=False):
+    """utils/frame_utils.py:138-164.  image: float32 H x W (or H x W x 3 / H x W x 1) numpy array or tensor; rows are
+    flipped here unless the caller already did (``disp_to_depth(..., flip_rows=True)``)."""
+    if isinstance(image, torch.Tensor):
+        image = image.detach().cpu().numpy()
+    if image.dtype.name != "float32":
+        raise Exception("Image dtype must be float32.")
+    if not flipped:
+        image = np.flipud(image)
+    if len(image.shape) == 3 and image.shape[2] == 3:
+        color = True
+    elif len(image.shape) == 2 or len(image.shape) == 3 and image.shape[2] == 1:
+        color = False
+    else:
+        raise Exception("Image must have H x W x 3, H x W x 1 or H x W dimensions.")
+    endian = image.dtype.byteorder
+    if endian == "<" or endian == "=" and sys.byteorder == "little":
+        scale = -scale
+    with open(file, "wb") as f:
+        f.write(b"PF\n" if color else b"Pf\n")
+        f.write(b"%d %d\n" % (image.shape[1], image.shape[0]))
+        f.write(b"%f\n" % scale)
+        np.ascontiguousarray(image).tofile(f)
+
+
+def readPFM(file):
+    """utils/frame_utils.py:10-40: returns the image top-down (float32, H x W or H x W x 3)."""
+    with open(file, "rb") as f:
+        header = f.readline().rstrip()
+        if header == b"PF":
+            color = True
+        elif header == b"Pf":
+            color = False
+        else:
+            raise Exception("Not a PFM file.")
+        m = re.match(rb"^(\d+)\s(\d+)\s$", f.readline())
+        if not m:
+            raise Exception("Malformed PFM header.")
+        width, height = map(int, m.groups())
+        scale = float(f.readline().rstrip())
+        endian = "<" if scale < 0 else ">"
+        data = np.fromfile(f, endian + "f")
+    shape = (height, width, 3) if color else (height, width)
+    return np.flipud(np.reshape(data, shape))

@@ -141,6 +141,23 @@ int cer_set_lookup_variant(int variant);
 /* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */
 int cer_debug_set_conv_profile(void* dev_buf);
 
+/* ---- image preparation, depth output, multi-resolution merge (csrc/io_ops.cu) ---------------- */
+
+/* images *= 2 / 255.; images -= 1 (core/raft.py:40-41), n floats, src may equal dst. */
+int cer_normalize_images(const float* src, float* dst, long long n, cer_stream_t stream);
+
+/* F.interpolate(images, [h2, w2], mode='bilinear', align_corners=True) of `planes` h x w planes
+ * (scale_operation, utils/data_utils.py:58-66: the rescale=2 pass of the cascaded configuration). */
+int cer_resize_bilinear_ac(const float* src, float* dst, int planes, int h, int w, int h2, int w2, cer_stream_t stream);
+
+/* depth = where(disp == 0, 0, 1 / disp) (inference.py:57-58); flip_rows != 0 stores row y at row h-1-y, the order
+ * write_pfm puts on disk (utils/frame_utils.py:145).  In place (depth == disp) only without the flip. */
+int cer_disp_to_depth(const float* disp, float* depth, int h, int w, int flip_rows, cer_stream_t stream);
+
+/* multires.py:26-28: im1r = cv2.resize(im1, (w2, h2)) (INTER_LINEAR); out = |im1r - im2| < th * im1r ? im2 : im1r. */
+int cer_multires_merge(const float* im1, int h1, int w1, const float* im2, int h2, int w2, float th, float* out,
+                       cer_stream_t stream);
+
 /* ConvGRU.forward alone (core/update.py:17-25): net [h*w,64] fp16 NHWC updated in place from
  * inputs inp [h*w,64], dn [h*w,64] (49 disparity-encoder channels + 15 zero), e [h*w,64], all fp16 NHWC. */
 int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e,

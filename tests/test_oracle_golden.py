@@ -91,3 +91,23 @@ def test_e2e_autocast_emulation(golden):
     out, ref, _, _ = _e2e(golden, "e2e_autocast_drift", autocast=True)
     err = rel_l1(out, ref)
     assert err < 1e-3, err
+
+
+def test_io_oracle_matches_reference_functions(golden):
+    """oracle/io_oracle.py against outputs of the reference's scale_operation / write_pfm / multires()."""
+    import io_oracle as IO
+    g = golden("ops_io")
+    for name, s in (("s2", 2), ("s15", 1.5)):
+        out, K = IO.scale_operation(g["scale_in"], g["scale_K_in"], s)
+        np.testing.assert_allclose(out, g[f"scale_{name}_out"], rtol=2e-6, atol=2e-5)
+        np.testing.assert_array_equal(K, g[f"scale_{name}_K"])
+    np.testing.assert_array_equal(IO.normalize_images(g["scale_in"]), g["norm_out"])
+    np.testing.assert_array_equal(IO.disp_to_depth(g["disp"]), g["depth"])
+    assert IO.pfm_bytes(g["depth"]) == g["pfm_bytes"].tobytes()
+    merged, im1r = IO.multires_merge(g["multires_im1"], g["multires_im2"], 0.02)
+    # the select is discontinuous: compare away from the decision boundary |im1r - im2| == th * im1r
+    margin = np.abs(np.abs(im1r - g["multires_im2"]) - np.float32(0.02) * im1r) > 1e-3
+    assert margin.mean() > 0.99
+    np.testing.assert_allclose(merged[margin], g["multires_out"][margin], rtol=1e-6)
+    picked2 = g["multires_out"] == g["multires_im2"]
+    assert 0.2 < picked2.mean() < 0.8                 # both branches of the select are exercised
