@@ -64,7 +64,10 @@ struct TcCfg {
   static constexpr bool CG2 = MODE == TC_CG2;
   static constexpr bool MC2 = MODE == TC_MC2;
   static constexpr int MT = MODE == TC_MT2 ? 2 : 1;             // M tiles per CTA work unit
-  static constexpr bool RESIDENT = (N == 64);                 // all 9 weight tiles stay in smem
+  // all 9 weight tiles stay in smem: the N = 64 convs, and the delta conv (N = 256) as a CTA pair -- each CTA's half of
+  // its 288 KB weight set is 144 KB, exactly the three 3-tap stages the pair form has room for, so the pair never
+  // re-streams weights (the 1-CTA form pulls 295 KB per 128-pixel tile through its L2 port for only 36 MMAs)
+  static constexpr bool RESIDENT = (N == 64) || (MODE == TC_CG2 && N == 256);
   // taps per weight stage: the CTA-pair form moves a whole kernel row (3 taps) per stage so that the issuing thread
   // pays one barrier wait + one commit per 12 MMAs instead of per 4 (its per-step cost, not the tensor pipe, bounds
   // the streamed-weight convs); the pair's halved weight footprint is what makes room for it
@@ -72,7 +75,7 @@ struct TcCfg {
   static_assert(!S3 || N == 192, "3-tap stages of the 1-CTA form are sized for the gate conv");
   static constexpr int TPS = (CG2 || S3) ? 3 : 1;
   static constexpr int NG = 9 / TPS;                          // stages per 64-channel chunk
-  static constexpr int NB = RESIDENT ? 9 : S3 ? 2 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
+  static constexpr int NB = RESIDENT ? NG : S3 ? 2 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
   static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
   // A ring depth (64-channel chunks).  Deeper rings / more accumulator stages for the N = 64 convs were measured
   // slower (q/GRU 36 -> 44 us): those kernels are bound by their per-tile latency chain, not by ring capacity.
@@ -162,7 +165,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
   constexpr int MT = C::MT;
   static_assert(MT == 1 || (!C::RESIDENT && N * 2 <= 512), "MT2 is for the streamed-weight convs");
   static_assert(!(MC2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
-  static_assert(!(CG2 && C::RESIDENT), "resident weights are only used by the 1-CTA form");
   static_assert(!CG2 || C::NB >= C::NA, "the CTA pair reuses bar_b_peer(0..NA) as peer-A-full barriers");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s0 = smem_u32(smem);
@@ -364,9 +366,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
     if (lane == 0) {
       const char* wsrc = reinterpret_cast<const char*>(CG2 ? a.wtc2 : a.wtc);
       if (C::RESIDENT) {
-        for (int s = 0; s < 9; ++s) {
-          mbar_expect_tx(bar_b_full(s), C::B_BYTES);
-          bulk_g2s(sB + s * C::B_BYTES, wsrc + (size_t)s * C::B_BYTES, C::B_BYTES, bar_b_full(s));
+        for (int s = 0; s < C::NG; ++s) {      // loaded once, never released
+          if (CG2) {
+            if (rank == 0) mbar_expect_tx(bar_b_full(s), 2 * C::STAGE_BYTES);
+#pragma unroll
+            for (int kx = 0; kx < C::TPS; ++kx)
+              tma2d_cg2(sB + s * C::STAGE_BYTES + kx * C::B_BYTES, &wmap, 0,
+                        ((s * C::TPS + kx) * 2 + (int)rank) * (C::B_BYTES / 256), bar_b_full(s));
+          } else {
+            mbar_expect_tx(bar_b_full(s), C::STAGE_BYTES);
+            bulk_g2s(sB + s * C::STAGE_BYTES, wsrc + (size_t)s * C::STAGE_BYTES, C::STAGE_BYTES, bar_b_full(s));
+          }
         }
       } else {
         int seq = 0;
@@ -522,15 +532,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
       // operands of the element-wise GRU algebra do not depend on the accumulator: fetch them before waiting for it
       uint4 pre_a[4];
       if (EPI == EPI_GATES && ok) ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);   // net slice of this thread's r chunk
-      uint4 pre_z[4];
-      float4 pre_q[8];
-      if (EPI == EPI_GRUOUT && ok) {          // z, net and the x-part of q for this thread's 32 channels (N = 64: cb == chalf)
-        ldg_half32_raw(a.z + p * 64 + chalf * 32, pre_z);
-        ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);
-        const float4* q = reinterpret_cast<const float4*>(a.qx + p * 64 + chalf * 32);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) pre_q[e] = q[e];
-      }
       if (j == 0) pwait(bar_acc_full(as), (t / C::NACC) & 1, 0);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * N) + j * N;
@@ -578,19 +579,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           }
         } else if (EPI == EPI_GRUOUT) {
           if (ok) {
-            // 8 channels at a time straight from the packed prefetch registers (keeps the live set under 128 registers)
-            const uint32_t* zp = reinterpret_cast<const uint32_t*>(pre_z);
-            const uint32_t* np_ = reinterpret_cast<const uint32_t*>(pre_a);
+            // (prefetching z / net / qx before the accumulator wait was measured slower: 39 vs 36 us -- the extra 64 live
+            // registers spill and the loads are L2 hits that the eight epilogue warps already overlap)
+            float zz[32], nt[32];
+            ld_half32(a.z + p * 64 + n0, zz);
+            ld_half32(a.net + p * 64 + n0, nt);
+            const float4* q = reinterpret_cast<const float4*>(a.qx + p * 64 + n0);
 #pragma unroll
-            for (int e2 = 0; e2 < 16; ++e2) {
-              const float2 zz = __half22float2(*reinterpret_cast<const __half2*>(&zp[e2]));
-              const float2 nt = __half22float2(*reinterpret_cast<const __half2*>(&np_[e2]));
-              const float4 qq = pre_q[e2 >> 1];
-              const float qa = (e2 & 1) ? qq.z : qq.x, qb = (e2 & 1) ? qq.w : qq.y;
-              const float q0 = h_round(fast_tanh(h_round(v[2 * e2] + qa)));
-              const float q1 = h_round(fast_tanh(h_round(v[2 * e2 + 1] + qb)));
-              v[2 * e2] = h_round(h_round(h_round(1.f - zz.x) * nt.x) + h_round(zz.x * q0));
-              v[2 * e2 + 1] = h_round(h_round(h_round(1.f - zz.y) * nt.y) + h_round(zz.y * q1));
+            for (int e = 0; e < 8; ++e) {
+              const float4 qq = q[e];
+              v[4 * e] += qq.x; v[4 * e + 1] += qq.y; v[4 * e + 2] += qq.z; v[4 * e + 3] += qq.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float qv = h_round(fast_tanh(h_round(v[e])));
+              v[e] = h_round(h_round(h_round(1.f - zz[e]) * nt[e]) + h_round(zz[e] * qv));
             }
             st_half32(a.net + p * 64 + n0, v);
           }
