@@ -228,6 +228,15 @@ struct Slice16 {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
   }
+  // load only if `need` (a predicated-off lane sends nothing to L1); the registers keep zeros otherwise
+  __device__ __forceinline__ void load_if(const void* p, bool need) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0u;
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %9, 0;\n"
+                 " @q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n}"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+                 : "l"(p), "r"((uint32_t)need));
+  }
   __device__ __forceinline__ float dot(const Slice16& o) const {
     float d = fhfma_lo(v[0], o.v[0], 0.f);
     d = fhfma_hi(v[0], o.v[0], d);
@@ -242,7 +251,13 @@ struct Slice16 {
 
 constexpr int kH16Chunks = 4;   // chunks of 4 hypotheses per block in sequence
 
-__global__ void __launch_bounds__(256) build_volume_h16_kernel(
+// REUSE: consecutive hypotheses of a pixel that land in the same or a neighbouring source cell (the second cascade stage
+// steps ~0.7 source pixels per hypothesis) share corner rows, and the dot of the reference pixel with a corner row does
+// not depend on the hypothesis: the four dots of the previous sample are kept and a corner whose row was already seen
+// is not fetched again (its load is predicated off, so it costs no L1 wavefront -- the limiter of this kernel).  Same
+// operands in the same order, so the result is bit-identical.
+template <bool REUSE>
+__global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
     const __half* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
     const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
     float lo_origin, float* __restrict__ origin_out, float* __restrict__ volume, float out_scale, int per_view,
@@ -318,19 +333,44 @@ __global__ void __launch_bounds__(256) build_volume_h16_kernel(
       }
       __syncwarp();
       float part[4];
+      int4 po = make_int4(-1, -1, -1, -1);          // corner rows (byte offsets) and dots of the previous sample
+      float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int4 o4 = *reinterpret_cast<const int4*>(grp + s * 8);
         const float4 wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
-        Slice16 f2;
-        f2.load(ptr_add_u32(img2, (uint32_t)o4.x));
-        const float d00 = f1.dot(f2);
-        f2.load(ptr_add_u32(img2, (uint32_t)o4.y));
-        const float d01 = f1.dot(f2);
-        f2.load(ptr_add_u32(img2, (uint32_t)o4.z));
-        const float d10 = f1.dot(f2);
-        f2.load(ptr_add_u32(img2, (uint32_t)o4.w));
-        const float d11 = f1.dot(f2);
+        float d00, d01, d10, d11;
+        if (REUSE) {
+          // which corners were seen by the previous sample (uniform over the 4 lanes of a pixel)
+          auto seen = [&](int off, float& d) {
+            const bool hx = off == po.x, hy = off == po.y, hz = off == po.z, hw = off == po.w;
+            d = hx ? pd.x : hy ? pd.y : hz ? pd.z : pd.w;
+            return hx || hy || hz || hw;
+          };
+          float c00, c01, c10, c11;
+          const bool h00 = seen(o4.x, c00), h01 = seen(o4.y, c01), h10 = seen(o4.z, c10), h11 = seen(o4.w, c11);
+          Slice16 a, b, c, e;                        // all needed loads in flight together
+          a.load_if(ptr_add_u32(img2, (uint32_t)o4.x), !h00);
+          b.load_if(ptr_add_u32(img2, (uint32_t)o4.y), !h01);
+          c.load_if(ptr_add_u32(img2, (uint32_t)o4.z), !h10);
+          e.load_if(ptr_add_u32(img2, (uint32_t)o4.w), !h11);
+          d00 = h00 ? c00 : f1.dot(a);
+          d01 = h01 ? c01 : f1.dot(b);
+          d10 = h10 ? c10 : f1.dot(c);
+          d11 = h11 ? c11 : f1.dot(e);
+          po = o4;
+          pd = make_float4(d00, d01, d10, d11);
+        } else {
+          Slice16 f2;
+          f2.load(ptr_add_u32(img2, (uint32_t)o4.x));
+          d00 = f1.dot(f2);
+          f2.load(ptr_add_u32(img2, (uint32_t)o4.y));
+          d01 = f1.dot(f2);
+          f2.load(ptr_add_u32(img2, (uint32_t)o4.z));
+          d10 = f1.dot(f2);
+          f2.load(ptr_add_u32(img2, (uint32_t)o4.w));
+          d11 = f1.dot(f2);
+        }
         part[s] = ((d00 * wt.x) * wt.z + (d01 * wt.x) * wt.w) + ((d10 * wt.y) * wt.z + (d11 * wt.y) * wt.w);
       }
       __syncwarp();
@@ -361,6 +401,15 @@ namespace cer {
 int build_volume_tc(const void* feats, const float* Pij, const int* ii, const int* jj, int n_pairs,
                     const float* disp_in, int shift, int D, float incre, float lo_origin, float* origin,
                     float* volume, float out_scale, int per_view, int h, int w, cudaStream_t stream);
+// corner-dot reuse in the FHFMA build kernel: -1 = automatic (refinement stages only), 0 = never, 1 = always (CER_BUILD_REUSE)
+static int g_build_reuse = -2;
+static int build_reuse() {
+  if (g_build_reuse == -2) {
+    const char* e = getenv("CER_BUILD_REUSE");
+    g_build_reuse = e ? atoi(e) : -1;
+  }
+  return g_build_reuse;
+}
 static int g_build_variant = -1;
 static int build_variant() {
   if (g_build_variant < 0) {
@@ -377,6 +426,12 @@ extern "C" int cer_set_build_variant(int variant) {
   CER_REQUIRE(variant >= 0 && variant <= 2,
               "cer_set_build_variant: 0 FHFMA gather, 4 lanes x 256-bit loads (default); 1 tcgen05 gather; 2 FHFMA gather, 8 lanes");
   g_build_variant = variant;
+  return CER_OK;
+}
+
+extern "C" int cer_set_build_reuse(int mode) {
+  CER_REQUIRE(mode >= -1 && mode <= 1, "cer_set_build_reuse: -1 automatic (refinement stages), 0 never, 1 always");
+  g_build_reuse = mode;
   return CER_OK;
 }
 
@@ -397,8 +452,15 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
   if (feats_f16 && build_variant() != 2) {
     dim3 g16(((w + 7) / 8) * ((h + 7) / 8), ceil_div(ceil_div(D, 4), kH16Chunks));
-    CER_LAUNCH(KK_BUILD, build_volume_h16_kernel, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
-               shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+    // corner-dot reuse pays when neighbouring hypotheses fall into neighbouring source cells: the refinement stages
+    // (no origin shift, fine increments); the first stage steps several source pixels per hypothesis
+    const bool reuse = build_reuse() == 1 || (build_reuse() < 0 && !shift);
+    if (reuse)
+      CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<true>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
+                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+    else
+      CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<false>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
+                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
   } else if (feats_f16)
     CER_LAUNCH(KK_BUILD, build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
                shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);

@@ -81,6 +81,11 @@ int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const i
  * (needs D >= 43; CER_BUILD=tc).  fp32 features always use the 8-lane kernel with plain FFMA. */
 int cer_set_build_variant(int variant);
 
+/* Corner-dot reuse between consecutive hypotheses in the FHFMA build kernel (fp16 features): -1 = automatic (stages
+ * without origin shift, i.e. the fine refinement stages; default), 0 = never, 1 = always.  Results are bit-identical;
+ * only the number of corner rows fetched through L1 changes (CER_BUILD_REUSE). */
+int cer_set_build_reuse(int mode);
+
 /* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
 int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stream_t stream);
 
@@ -123,10 +128,11 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     cer_stream_t stream);
 
 /* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on all of them):
- *   6 = default (CER_CONV unset): tcgen05.mma + TMEM, persistent CTAs; the gate conv (N = 192) as CTA pairs issuing
- *       cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), every other conv one 128-pixel tile per CTA
+ *   1 = default (CER_CONV unset or tc2): tcgen05.mma + TMEM, persistent CTAs; the two wide convs as CTA pairs issuing
+ *       cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile; the delta conv keeps its half weight
+ *       set resident), the N = 64 convs one 128-pixel tile per CTA with resident weights
+ *   6 = CTA pairs for the gate conv only, the delta conv one tile per CTA
  *   2 = every conv one 128-pixel tile per CTA at a time (CER_CONV=tc1)
- *   1 = both N >= 192 convolutions as cta_group::2 CTA pairs (CER_CONV=tc2)
  *   3 = the N >= 192 convolutions as 2-CTA clusters that multicast each weight tile
  *   4 = the N >= 192 convolutions with two 128-pixel tiles per CTA sharing each weight stage
  *   5 = the gate conv with a whole kernel row (3 taps) per weight stage, one tile per CTA

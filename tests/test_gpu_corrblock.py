@@ -136,6 +136,23 @@ def test_lookup_variants_bit_identical(golden, stage, build_variant):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("stage", [0, 1])
+def test_build_corner_reuse_bit_identical(golden, stage, build_variant):
+    """Re-using the dots of corner rows shared with the previous hypothesis changes what is fetched, not what is summed."""
+    if build_variant != "fhfma":
+        pytest.skip("the FHFMA 4-lane kernel only")
+    from cer_mvs_b200 import _lib
+    vols = {}
+    try:
+        for mode in (0, 1):
+            _lib.check(_lib.lib().cer_set_build_reuse(mode))
+            cb, _ = _block(golden, stage, per_view=False, dtype=torch.float16)
+            vols[mode] = cb.volume.cpu().numpy()
+    finally:
+        _lib.lib().cer_set_build_reuse(-1)
+    assert np.array_equal(vols[0], vols[1])
+
+
 def test_identity_view_known_answer():
     """Source view == reference view with the same pose: every hypothesis reprojects onto the pixel
     itself, so the volume is |f|^2/64 for every d (size-independent known answer)."""
