@@ -401,12 +401,15 @@ namespace cer {
 int build_volume_tc(const void* feats, const float* Pij, const int* ii, const int* jj, int n_pairs,
                     const float* disp_in, int shift, int D, float incre, float lo_origin, float* origin,
                     float* volume, float out_scale, int per_view, int h, int w, cudaStream_t stream);
-// corner-dot reuse in the FHFMA build kernel: -1 = automatic (refinement stages only), 0 = never, 1 = always (CER_BUILD_REUSE)
+// corner-dot reuse in the FHFMA build kernel: 0 = never (default), 1 = always, -1 = refinement stages only
+// (CER_BUILD_REUSE).  Measured on B200 (cfg 2): it removes ~45 % of the stage-1 corner fetches but needs 80 registers
+// (3 CTAs per SM instead of 4) and 36 more instructions per sample: 1.83 ms / stage against 1.75 ms without it --
+// the kernel is bound by the latency of its L1 misses at the occupancy it has, not by L1 wavefronts alone.
 static int g_build_reuse = -2;
 static int build_reuse() {
   if (g_build_reuse == -2) {
     const char* e = getenv("CER_BUILD_REUSE");
-    g_build_reuse = e ? atoi(e) : -1;
+    g_build_reuse = e ? atoi(e) : 0;
   }
   return g_build_reuse;
 }
@@ -452,8 +455,8 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
   if (feats_f16 && build_variant() != 2) {
     dim3 g16(((w + 7) / 8) * ((h + 7) / 8), ceil_div(ceil_div(D, 4), kH16Chunks));
-    // corner-dot reuse pays when neighbouring hypotheses fall into neighbouring source cells: the refinement stages
-    // (no origin shift, fine increments); the first stage steps several source pixels per hypothesis
+    // corner-dot reuse (opt-in experiment, see build_reuse()): neighbouring hypotheses of the refinement stages fall
+    // into neighbouring source cells; the first stage steps several source pixels per hypothesis
     const bool reuse = build_reuse() == 1 || (build_reuse() < 0 && !shift);
     if (reuse)
       CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<true>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,

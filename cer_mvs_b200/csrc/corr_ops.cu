@@ -427,7 +427,7 @@ int cer_lookup_strided(const float* volume, int slots, const float* origin, cons
   CER_REQUIRE((D >> (num_levels - 1)) >= 2, "cer_lookup: D too small for %d levels", num_levels);
   CER_REQUIRE(D <= 1024, "cer_lookup: D > 1024 unsupported");
   const long long px = (long long)h * w;
-  if (lookup_variant() == 2 && radius == 5 && num_levels == 3 && (D == 64 || D == 44) && px < (1ll << 31) - 64) {
+  if (lookup_variant() >= 2 && radius == 5 && num_levels == 3 && (D == 64 || D == 44) && px < (1ll << 31) - 64) {
     static bool configured = false;
     const size_t smem2 = (size_t)kLookupV2Warps * kPyrWarpFloats * sizeof(float);
     if (!configured) {

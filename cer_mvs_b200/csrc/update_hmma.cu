@@ -417,6 +417,152 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
   }
 }
 
+// KA v3: v2 with the level-0 rows only in shared memory (9.3 KB per warp, levels 1-2 pooled on the fly from the zero
+// padded row) and a register cap of 102: 20 resident warps per SM instead of 12.  ncu on v2: 17 % of the warp slots
+// active, every warp a long dependent chain -- the kernel wants more warps, not fewer instructions.
+static_assert(32 * kA1Pitch * 2 + 32 * kL2_OUT_PITCH <= kPyr0WarpFloats * 4, "A tile + e1 staging tile alias the level-0 rows");
+template <int D>
+__global__ void __launch_bounds__(kL2_WARPS * 32, 5) lookup_enc1_v3_kernel(
+    const float* __restrict__ volume, const float* __restrict__ origin, float* __restrict__ disp,
+    const float* __restrict__ s9, int parts, const float* __restrict__ bd1, int apply_prev, float incre,
+    const __half* __restrict__ w1, const float* __restrict__ b1, __half* __restrict__ e1, int h, int w) {
+  static_assert(D % 4 == 0 && D <= 64 && D >= 8, "row registers / pitches are sized for D <= 64, 16-byte row pieces");
+  constexpr int NV = D / 4;                                  // 16-byte pieces per pixel row = row loads per lane
+  extern __shared__ __align__(16) unsigned char fsm[];
+  __half* sW = reinterpret_cast<__half*>(fsm);                                   // [48][kW1Pitch]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* L0 = reinterpret_cast<float*>(fsm + kCorrK * kW1Pitch * 2) + warp * kPyr0WarpFloats;
+  const int px = h * w;
+  // a warp past the end of the image (last CTA only) runs on pixel 0 with npix = 0: every store is guarded by npix, and
+  // the CTA keeps one barrier for all warps
+  const int p0_raw = (blockIdx.x * kL2_WARPS + warp) * 32;
+  const int p0 = p0_raw < px ? p0_raw : 0;
+  pdl_trigger();
+  // 1x1 weights: constants, requested before the dependency wait; they are parked in registers until the chunk's own
+  // loads are in flight too, so a CTA pays ONE global-latency exposure, not two (ncu: 20 % of the v2 kernel's stall
+  // samples sat on the weight store that used to come first)
+  constexpr int WQ = kCorrK * kHid / 8 / (kL2_WARPS * 32);
+  static_assert(WQ * kL2_WARPS * 32 * 8 == kCorrK * kHid, "weight pieces divide evenly over the CTA");
+  uint4 wreg[WQ];
+#pragma unroll
+  for (int q = 0; q < WQ; ++q) wreg[q] = __ldg(reinterpret_cast<const uint4*>(w1) + q * kL2_WARPS * 32 + tid);
+  pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
+  const int npix = p0_raw < px ? min(32, px - p0) : 0;
+  const bool live = lane < npix;
+  const int p = p0 + (live ? lane : 0);
+
+  // ---- issue every load of the chunk ----
+  float4 rv[NV];
+  pyr_load_chunk<D>(volume + (long long)p0 * D, npix, lane, rv);
+  float dsp = disp[p];
+  const float org = __ldg(origin + p);
+  float sv[9];
+  if (apply_prev) {     // K6 of the previous iteration: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t]))
+    const int x = p % w, y = p / w;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      sv[t] = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
+        sv[t] = (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int q = 0; q < WQ; ++q) {
+    const int i = q * kL2_WARPS * 32 + tid;
+    *reinterpret_cast<uint4*>(sW + (i / (kHid / 8)) * kW1Pitch + (i % (kHid / 8)) * 8) = wreg[q];
+  }
+  // ---- pyramid rows -> shared memory ----
+  pyr0_store_chunk<D>(rv, L0, lane);
+  if (apply_prev) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int x = p % w, y = p / w;
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += sv[t];
+    }
+    dsp += h_round(0.01f * h_round(s + __ldg(bd1)));
+    if (live) disp[p] = dsp;
+  }
+  const float c = live ? lookup_coord(dsp, org, incre, D) : 0.f;
+  __syncwarp();
+
+  // ---- 33 taps of this lane's pixel -> fp16 A row (registers) ----
+  uint32_t arow[kCorrK / 2];
+  {
+    float tp33[33], tp[kCorrK];
+    pyr0_taps33<D>(L0, lane, c, tp33);
+#pragma unroll
+    for (int k = 0; k < kCorrPlanes; ++k) tp[k] = tp33[k];
+#pragma unroll
+    for (int k = kCorrPlanes; k < kCorrK; ++k) tp[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCorrK / 2; ++k) {
+      const __half2 hh = __floats2half2_rn(live ? tp[2 * k] : 0.f, live ? tp[2 * k + 1] : 0.f);
+      arow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+  }
+  __syncwarp();                       // every lane is done with the pyramid rows: the A tile may overwrite level 0
+  __half* sA = reinterpret_cast<__half*>(L0);
+#pragma unroll
+  for (int k = 0; k < kCorrK / 8; ++k)
+    *reinterpret_cast<uint4*>(sA + lane * kA1Pitch + k * 8) =
+        make_uint4(arow[4 * k], arow[4 * k + 1], arow[4 * k + 2], arow[4 * k + 3]);
+  __syncthreads();                    // the only CTA barrier: the 1x1 weights of all four warps are in place (and my A tile)
+
+  // ---- 1x1 conv on mma.sync (two 16-pixel tiles), bias, fp16 rounding, ReLU -> staging tile ----
+  unsigned char* sO = reinterpret_cast<unsigned char*>(L0) + 32 * kA1Pitch * 2;     // behind the A tile
+  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * kW1Pitch + 8 * (lane >> 4)) * 2;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    const uint32_t aBase = smem_u32(sA) + ((mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kA1Pitch + 8 * (lane >> 4)) * 2;
+#pragma unroll
+    for (int k16 = 0; k16 < kCorrK / 16; ++k16) {
+      uint32_t a[4];
+      ldmatrix_x4(a, aBase + k16 * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, bBase + (k16 * 16 * kW1Pitch + j * 16) * 2);
+        mma16816(acc[2 * j], a, b[0], b[1]);
+        mma16816(acc[2 * j + 1], a, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int row = mt * 16 + g + 8 * half;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = j * 8 + q * 2;
+        const float v0 = fmaxf(h_round(acc[j][2 * half] + __ldg(b1 + n)), 0.f);
+        const float v1 = fmaxf(h_round(acc[j][2 * half + 1] + __ldg(b1 + n + 1)), 0.f);
+        *reinterpret_cast<__half2*>(sO + row * kL2_OUT_PITCH + n * 2) = __floats2half2_rn(v0, v1);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- e1: 4 pixels (512 contiguous bytes) per warp store ----
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3), cchunk = lane & 7;
+    if (row < npix)
+      *reinterpret_cast<uint4*>(e1 + (long long)(p0 + row) * 64 + cchunk * 8) =
+          *reinterpret_cast<const uint4*>(sO + row * kL2_OUT_PITCH + cchunk * 16);
+  }
+}
+
+static size_t lookup_enc1_v3_smem() { return (size_t)kCorrK * kW1Pitch * 2 + (size_t)kL2_WARPS * kPyr0WarpFloats * 4; }
+
 static size_t lookup_enc1_v2_smem() { return (size_t)kCorrK * kW1Pitch * 2 + (size_t)kL2_WARPS * kL2_WARP_FLOATS * 4; }
 
 // ------------------------------------------------------------------------------------------
@@ -677,7 +823,7 @@ static int g_lookup_variant = -1;
 int lookup_variant() {
   if (g_lookup_variant < 0) {
     const char* e = getenv("CER_LOOKUP");
-    g_lookup_variant = (e && !strcmp(e, "v1")) ? 1 : 2;
+    g_lookup_variant = (e && !strcmp(e, "v1")) ? 1 : (e && !strcmp(e, "v2")) ? 2 : 3;
   }
   return g_lookup_variant;
 }
@@ -699,6 +845,10 @@ int update_configure() {
                                 (int)lookup_enc1_v2_smem()));
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v2_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)lookup_enc1_v2_smem()));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_v3_smem()));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_v3_smem()));
   done = true;
   return CER_OK;
 }
@@ -777,7 +927,17 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
   }
   const bool tc = conv_variant() == 1;
   // the two cascade widths of the reference (core/raft.py:77-81) take the warp-autonomous kernel; any other D the general one
-  if (lookup_variant() == 2 && (D == 64 || D == 44)) {
+  if (lookup_variant() == 3 && (D == 64 || D == 44)) {
+    const int grid = ceil_div(px, kL2_WARPS * 32);
+    if (D == 64)
+      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v3_kernel<64>, grid, kL2_WARPS * 32, lookup_enc1_v3_smem(), stream, volume, origin,
+                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
+                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
+    else
+      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v3_kernel<44>, grid, kL2_WARPS * 32, lookup_enc1_v3_smem(), stream, volume, origin,
+                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
+                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
+  } else if (lookup_variant() == 2 && (D == 64 || D == 44)) {
     const int grid = ceil_div(px, kL2_WARPS * 32);
     if (D == 64)
       CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v2_kernel<64>, grid, kL2_WARPS * 32, lookup_enc1_v2_smem(), stream, volume, origin,
@@ -947,7 +1107,8 @@ int cer_set_conv_variant(int variant) {
 }
 
 int cer_set_lookup_variant(int variant) {
-  CER_REQUIRE(variant == 1 || variant == 2, "cer_set_lookup_variant: 1 block-staged kernel, 2 warp-autonomous kernel (default)");
+  CER_REQUIRE(variant >= 1 && variant <= 3,
+              "cer_set_lookup_variant: 1 block-staged kernel, 2 warp-autonomous kernel, 3 warp-autonomous, level-0 rows only (default)");
   set_lookup_variant(variant);
   return CER_OK;
 }

@@ -38,6 +38,9 @@ constexpr int TC_W_MMA2 = TC_W_APROD + TC_PROD / 32;            // warp 13: dn p
 constexpr int TC_W_DN = TC_W_MMA2;                               // warps 13-15: dn producers
 constexpr int TC_DN = 96;                                        // dn producer threads (== TC_PROD: same arrival count)
 constexpr int TC_THREADS = TC_W_DN * 32 + TC_DN;                 // 512
+// only the gate conv has a dn chunk: the other convs are launched without the three dn warps (416 threads), which frees
+// three idle warps' worth of registers and scheduler slots
+__host__ __device__ constexpr int tc_threads(int epi) { return epi == EPI_GATES ? TC_THREADS : TC_W_DN * 32; }
 // Two issuer warps taking alternate (chunk, tap) steps buy ~5 % on the gate conv but make the fp32 accumulation order
 // (and therefore the last bit of some outputs) depend on how the two warps interleave: off, results are bit-reproducible.
 constexpr bool kTwoIssuers = false;      // (warp 13 generates the dn chunk instead)
@@ -158,7 +161,7 @@ __device__ __forceinline__ void ld_half32(const __half* src, float (&v)[32]) {
 
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int N, int EPI, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArgs a,
+__global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const ConvArgs a,
                                                                   const __grid_constant__ CUtensorMap wmap) {
   using C = TcCfg<N, MODE>;
   constexpr bool CG2 = C::CG2, MC2 = C::MC2;
@@ -579,8 +582,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const ConvArg
           }
         } else if (EPI == EPI_GRUOUT) {
           if (ok) {
-            // (prefetching z / net / qx before the accumulator wait was measured slower: 39 vs 36 us -- the extra 64 live
-            // registers spill and the loads are L2 hits that the eight epilogue warps already overlap)
+            // (prefetching z / net / qx before the accumulator wait was measured slower: 39 vs 36 us -- ptxas holds this
+            // kernel at 128 registers, the extra 64 live registers spill, and the loads are L2 hits that the eight
+            // epilogue warps already overlap)
             float zz[32], nt[32];
             ld_half32(a.z + p * 64 + n0, zz);
             ld_half32(a.net + p * 64 + n0, nt);
@@ -742,7 +746,7 @@ static int launch_pair(const ConvArgs& a, int tiles, int kind, cudaStream_t stre
   grid &= ~1;                                             // whole CTA pairs
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(tc_threads(EPI));
   cfg.dynamicSmemBytes = TcCfg<N, MODE>::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -777,7 +781,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
     const int grid = units < kNumSMs ? units : kNumSMs;
     CUtensorMap nomap;
     memset(&nomap, 0, sizeof(nomap));
-    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, TC_THREADS, (TcCfg<N, M3>::TOTAL), stream, a, nomap);
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, tc_threads(EPI), (TcCfg<N, M3>::TOTAL), stream, a, nomap);
     return check_launch("conv3x3_tc");
   }
   if (N == 192 && g_pair_mode == TC_S3) {
@@ -785,7 +789,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     CUtensorMap nomap;
     memset(&nomap, 0, sizeof(nomap));
-    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M4>), grid, TC_THREADS, (TcCfg<N, M4>::TOTAL), stream, a, nomap);
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M4>), grid, tc_threads(EPI), (TcCfg<N, M4>::TOTAL), stream, a, nomap);
     return check_launch("conv3x3_tc");
   }
   if (N != 64 && tiles >= 2 && g_pair_mode != TC_SINGLE && g_pair_mode != TC_S3) {
@@ -796,7 +800,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
   CUtensorMap nomap;
   memset(&nomap, 0, sizeof(nomap));
-  CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, TC_SINGLE>), grid, TC_THREADS, (TcCfg<N, TC_SINGLE>::TOTAL), stream, a,
+  CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, TC_SINGLE>), grid, tc_threads(EPI), (TcCfg<N, TC_SINGLE>::TOTAL), stream, a,
                  nomap);
   return check_launch("conv3x3_tc");
 }

@@ -81,9 +81,9 @@ int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const i
  * (needs D >= 43; CER_BUILD=tc).  fp32 features always use the 8-lane kernel with plain FFMA. */
 int cer_set_build_variant(int variant);
 
-/* Corner-dot reuse between consecutive hypotheses in the FHFMA build kernel (fp16 features): -1 = automatic (stages
- * without origin shift, i.e. the fine refinement stages; default), 0 = never, 1 = always.  Results are bit-identical;
- * only the number of corner rows fetched through L1 changes (CER_BUILD_REUSE). */
+/* Corner-dot reuse between consecutive hypotheses in the FHFMA build kernel (fp16 features): 0 = never (default:
+ * measured slower on B200, see build_volume.cu), 1 = always, -1 = stages without origin shift only.  Results are
+ * bit-identical; only the number of corner rows fetched through L1 changes (CER_BUILD_REUSE). */
 int cer_set_build_reuse(int mode);
 
 /* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
@@ -140,8 +140,11 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
  * Takes effect for launches and graph captures issued afterwards. */
 int cer_set_conv_variant(int variant);
 
-/* Which fused lookup + 1x1-encoder kernel the plan uses (A/B switch): 2 = warp-autonomous kernel for the two cascade
- * widths D = 64 / 44 (default), 1 = the block-staged kernel (any D <= 256; CER_LOOKUP=v1).  Results are bit-identical. */
+/* Which lookup kernels are used (A/B switch; results are bit-identical):
+ *   3 = default: warp-autonomous kernels for the reference configuration (radius 5, 3 levels, D = 64 / 44); the plan's
+ *       fused lookup + 1x1-encoder kernel keeps only the level-0 rows in shared memory (20 warps per SM)
+ *   2 = the fused kernel with all three pyramid levels materialised in shared memory (12 warps per SM; CER_LOOKUP=v2)
+ *   1 = the general block-staged kernels only (any D <= 256 / any radius; CER_LOOKUP=v1). */
 int cer_set_lookup_variant(int variant);
 
 /* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */

@@ -131,7 +131,7 @@ def test_lookup_variants_bit_identical(golden, stage, build_variant):
             _lib.check(_lib.lib().cer_set_lookup_variant(v))
             outs[v] = [cb(t(g[f"s{stage}_z_{name}"]).cuda()[:, [0] * V]).cpu().numpy() for name in ("true", "zero", "far", "rand")]
     finally:
-        _lib.lib().cer_set_lookup_variant(2)
+        _lib.lib().cer_set_lookup_variant(3)
     for a, b in zip(outs[1], outs[2]):
         assert np.array_equal(a, b)
 
@@ -149,7 +149,7 @@ def test_build_corner_reuse_bit_identical(golden, stage, build_variant):
             cb, _ = _block(golden, stage, per_view=False, dtype=torch.float16)
             vols[mode] = cb.volume.cpu().numpy()
     finally:
-        _lib.lib().cer_set_build_reuse(-1)
+        _lib.lib().cer_set_build_reuse(0)
     assert np.array_equal(vols[0], vols[1])
 
 

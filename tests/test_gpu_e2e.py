@@ -163,12 +163,12 @@ def test_lookup_kernel_variants_bit_identical(golden, conv_variant):
     sc, sd, cascade = _inputs(g)
     outs = {}
     try:
-        for v in (1, 2):
+        for v in (1, 2, 3):
             _lib.check(_lib.lib().cer_set_lookup_variant(v))
             for graph in (True, False):
                 _, outs[(v, graph)] = _hot(sc, sd, cascade, g, torch.float16, use_graph=graph)
     finally:
-        _lib.lib().cer_set_lookup_variant(2)
+        _lib.lib().cer_set_lookup_variant(3)
     for k, o in outs.items():
         assert np.array_equal(o, outs[(1, True)]), k
     assert np.isfinite(outs[(2, True)]).all()

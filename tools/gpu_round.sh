@@ -14,7 +14,7 @@ timeout 400 python bench.py --steps 30 --warmup 3 > $OUT/${TAG}_bench_default.js
 for v in ${VARIANTS:-5 1}; do
   timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --conv-variant $v > $OUT/${TAG}_bench_conv$v.json 2> $OUT/${TAG}_bench_conv$v.err
 done
-CER_LOOKUP=v1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_lookupv1.json 2> $OUT/${TAG}_bench_lookupv1.err
+CER_LOOKUP=v2 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_lookupv2.json 2> $OUT/${TAG}_bench_lookupv2.err
 for f in $OUT/${TAG}_bench_*.json; do echo "== $f"; python - "$f" <<'PY'
 import json,sys
 try:
