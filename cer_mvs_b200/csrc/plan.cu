@@ -51,8 +51,9 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
                      int slots, float* delta, int apply_delta, int stage, int h, int w, cudaStream_t stream);
 int update_configure();
 int update_iteration_fused(const void* blob, void* workspace, void* net, const void* inp, float* disp,
-                           const float* volume, const float* origin, int D, float incre, int apply_prev, int stage,
-                           int h, int w, cudaStream_t stream);
+                           const float* volume, const float* origin, int D, float incre, int apply_prev, int iter,
+                           int stage, int h, int w, cudaStream_t stream);
+int update_reset_flags(void* workspace, int iters, int h, int w, cudaStream_t stream);
 int update_apply_delta(const void* blob, void* workspace, float* disp, int stage, int h, int w, cudaStream_t stream);
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, float s, long long n) {
@@ -259,11 +260,13 @@ float* cer_plan_partial_volume(cer_plan* p, int s, size_t* n_floats) {
 static int issue_iterations(cer_plan* p, int s, cudaStream_t stream) {
   const int D = p->cfg.D[s];
   const float incre = (float)p->cfg.incre[s];
+  int rc0 = update_reset_flags(p->ws, p->cfg.iters[s], p->cfg.h, p->cfg.w, stream);
+  if (rc0) return rc0;
   for (int it = 0; it < p->cfg.iters[s]; ++it) {
     // lookup of the current disparity fused with the corr encoder; the delta of the previous iteration is
     // applied inside the same kernel (core/raft.py:99-101)
     int rc = update_iteration_fused(p->blob, p->ws, p->net, p->inp, p->disp, p->volume, p->origin, D, incre,
-                                    it > 0, s, p->cfg.h, p->cfg.w, stream);
+                                    it > 0, it, s, p->cfg.h, p->cfg.w, stream);
     if (rc) return rc;
   }
   return update_apply_delta(p->blob, p->ws, p->disp, s, p->cfg.h, p->cfg.w, stream);

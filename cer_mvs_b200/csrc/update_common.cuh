@@ -29,15 +29,28 @@ struct ConvArgs {
   const float* w2;     // EPI_DELTA: [9][256]
   float* s9;           // EPI_DELTA: [px][2][9] partial dots of the second delta conv
   unsigned long long* prof;   // optional (tools/conv_roles.py): per-role wait/work cycle counters of CTA 0, else null
+  // Tile-level dependencies between consecutive tcgen05 convs of one iteration (same 16 x 8 tiling).  flags_out: this
+  // launch sets flags_out[tile] = 1 once every store of the tile is visible.  flags_in: instead of waiting for the whole
+  // upstream grid (griddepcontrol.wait), the roles that read its output wait for the 3 x 3 tile neighbourhood, so this
+  // grid's CTAs start on the SMs the upstream grid's tail leaves idle.  Both null: plain grid-level dependency.
+  int* flags_out;
+  const int* flags_in;
 };
+
+constexpr int kFlagIters = 64;      // iterations per stage with tile flags (later ones fall back to grid dependencies)
+constexpr int kFlagKernels = 3;     // corr-encoder 3x3, gates, q/GRU publish; gates, q/GRU, delta consume
+inline int flag_tiles(int h, int w) { return ((h + 15) / 16) * ((w + 7) / 8); }   // the tcgen05 convs' 16 x 8 tiling
 
 struct UpdateWs {
   __half *dn, *e1, *e, *z, *rnet;
   float *qx, *s9;
+  int* flags;                         // [kFlagIters][kFlagKernels][flag_tiles(h, w)]
+  size_t flags_bytes;
   size_t total;
 };
 
-inline UpdateWs carve_ws(void* base, long long px) {
+inline UpdateWs carve_ws(void* base, int h, int wd) {
+  const long long px = (long long)h * wd;
   UpdateWs w{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return (char*)base + r; };
@@ -48,12 +61,15 @@ inline UpdateWs carve_ws(void* base, long long px) {
   w.rnet = (__half*)take(px * 64 * 2);
   w.qx = (float*)take(px * 64 * 4);
   w.s9 = (float*)take(px * 18 * 4);   // [px][2 column halves][9 taps] (the mma.sync path fills half 0 only)
+  w.flags_bytes = (size_t)kFlagIters * kFlagKernels * flag_tiles(h, wd) * sizeof(int);
+  w.flags = (int*)take(w.flags_bytes);
   w.total = o;
   return w;
 }
 
 // tcgen05 variant (update_tc.cu)
 int tc_configure();
+int tc_num_tiles(int h, int w);
 template <int N, int EPI>
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream);
 int launch_conv_tc_dispatch(int n, int epi, const ConvArgs& a, cudaStream_t stream);

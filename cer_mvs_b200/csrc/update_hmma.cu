@@ -875,7 +875,7 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
   const BlobLayout L = blob_layout();
   const char* B = (const char*)blob;
   const long long px = (long long)h * w;
-  UpdateWs ws = carve_ws(workspace, px);
+  UpdateWs ws = carve_ws(workspace, h, w);
   int rc;
   if ((rc = update_configure())) return rc;
   const bool tc = conv_variant() == 1;
@@ -912,13 +912,33 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
 
 // One GRU iteration of the plan (core/raft.py:96-101): KA (apply pending delta, lookup, 1x1) + K2..K5.
 // The delta of THIS iteration stays pending in ws.s9 (applied by the next KA or by update_apply_delta).
+// Tile-level dependencies between the tcgen05 convs of an iteration (ConvArgs::flags_in / flags_out): 1 = on (default),
+// 0 = every kernel waits for its whole predecessor (CER_TILE_FLAGS=0 / cer_set_tile_flags).
+static int g_tile_flags = -1;
+static int tile_flags() {
+  if (g_tile_flags < 0) {
+    const char* e = getenv("CER_TILE_FLAGS");
+    g_tile_flags = (e && !strcmp(e, "0")) ? 0 : 1;
+  }
+  return g_tile_flags;
+}
+
+// Zero the tile flags of the next `iters` iterations (start of a stage; a memset node when captured).
+int update_reset_flags(void* workspace, int iters, int h, int w, cudaStream_t stream) {
+  if (conv_variant() != 1 || !tile_flags()) return CER_OK;
+  UpdateWs ws = carve_ws(workspace, h, w);
+  const size_t n = (size_t)(iters < kFlagIters ? iters : kFlagIters) * kFlagKernels * flag_tiles(h, w) * sizeof(int);
+  CER_CUDA(cudaMemsetAsync(ws.flags, 0, n, stream));
+  return CER_OK;
+}
+
 int update_iteration_fused(const void* blob, void* workspace, void* net, const void* inp, float* disp,
-                           const float* volume, const float* origin, int D, float incre, int apply_prev, int stage,
-                           int h, int w, cudaStream_t stream) {
+                           const float* volume, const float* origin, int D, float incre, int apply_prev, int iter,
+                           int stage, int h, int w, cudaStream_t stream) {
   const BlobLayout L = blob_layout();
   const char* B = (const char*)blob;
   const long long px = (long long)h * w;
-  UpdateWs ws = carve_ws(workspace, px);
+  UpdateWs ws = carve_ws(workspace, h, w);
   int rc;
   if ((rc = update_configure())) return rc;
   if (D > 256) {
@@ -926,6 +946,10 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
     return CER_ERR_INVALID;
   }
   const bool tc = conv_variant() == 1;
+  // tile flags of this iteration: [0] corr-encoder 3x3 -> gates, [1] gates -> q/GRU, [2] q/GRU -> delta
+  const bool flags_on = tc && tile_flags() && iter >= 0 && iter < kFlagIters;
+  const int n_flag_tiles = flag_tiles(h, w);
+  auto F = [&](int k) { return flags_on ? ws.flags + ((size_t)iter * kFlagKernels + k) * n_flag_tiles : (int*)nullptr; };
   // the two cascade widths of the reference (core/raft.py:77-81) take the warp-autonomous kernel; any other D the general one
   if (lookup_variant() == 3 && (D == 64 || D == 44)) {
     const int grid = ceil_div(px, kL2_WARPS * 32);
@@ -960,18 +984,22 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
   a.dn_chunk = -1;
   a.src[0] = ws.e1; a.n_src = 1; a.wpk = (const __half*)(B + L.w2); a.wtc = (const __half*)(B + L.t_w2);
   a.bias = (const float*)(B + L.b2); a.out_h = ws.e;
+  a.flags_in = nullptr; a.flags_out = F(0);
   if ((rc = launch_conv<64, EPI_RELU>(a, stream))) return rc;
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = ws.dn; a.src[3] = ws.e; a.n_src = 4;
   a.wpk = (const __half*)(B + L.wg); a.wtc = (const __half*)(B + L.t_wg); a.wtc2 = (const __half*)(B + L.p_wg); a.bias = (const float*)(B + L.bg);
   a.net = (__half*)net; a.z = ws.z; a.rnet = ws.rnet; a.qx = ws.qx;
   if (tc) { a.disp = disp; a.dn_chunk = 2; }
+  a.flags_in = F(0); a.flags_out = F(1);
   if ((rc = launch_conv<192, EPI_GATES>(a, stream))) return rc;
   a.dn_chunk = -1;
   a.src[0] = ws.rnet; a.n_src = 1; a.wpk = (const __half*)(B + L.wq); a.wtc = (const __half*)(B + L.t_wq); a.bias = nullptr;
+  a.flags_in = F(1); a.flags_out = F(2);
   if ((rc = launch_conv<64, EPI_GRUOUT>(a, stream))) return rc;
   a.src[0] = (const __half*)net; a.n_src = 1; a.wpk = (const __half*)(B + L.wd0[stage]);
   a.wtc = (const __half*)(B + L.t_wd0[stage]); a.wtc2 = (const __half*)(B + L.p_wd0[stage]); a.bias = (const float*)(B + L.bd0[stage]);
   a.w2 = (const float*)(B + L.wd1[stage]); a.s9 = ws.s9;
+  a.flags_in = F(2); a.flags_out = nullptr;
   return launch_conv<256, EPI_DELTA>(a, stream);
 }
 
@@ -980,7 +1008,7 @@ int update_apply_delta(const void* blob, void* workspace, float* disp, int stage
   const BlobLayout L = blob_layout();
   const char* B = (const char*)blob;
   const long long px = (long long)h * w;
-  UpdateWs ws = carve_ws(workspace, px);
+  UpdateWs ws = carve_ws(workspace, h, w);
   CER_LAUNCH_PDL(KK_DISP_UPDATE, disp_update_kernel, ceil_div(px, 256), 256, 0, stream, ws.s9, conv_variant() == 1 ? 2 : 1,
              (const float*)(B + L.bd1[stage]), disp, (float*)nullptr, 1, h, w);
   return check_launch("disp_update");
@@ -994,7 +1022,7 @@ extern "C" {
 
 size_t cer_update_blob_bytes(void) { return blob_layout().total; }
 
-size_t cer_update_workspace_bytes(int h, int w) { return carve_ws(nullptr, (long long)h * w).total; }
+size_t cer_update_workspace_bytes(int h, int w) { return carve_ws(nullptr, h, w).total; }
 
 int cer_pack_update_weights(const float* const* w, void* blob_host) {
   CER_REQUIRE(w && blob_host, "cer_pack_update_weights: null pointer");
@@ -1106,6 +1134,11 @@ int cer_set_conv_variant(int variant) {
   return CER_OK;
 }
 
+int cer_set_tile_flags(int on) {
+  g_tile_flags = on ? 1 : 0;
+  return CER_OK;
+}
+
 int cer_set_lookup_variant(int variant) {
   CER_REQUIRE(variant >= 1 && variant <= 3,
               "cer_set_lookup_variant: 1 block-staged kernel, 2 warp-autonomous kernel, 3 warp-autonomous, level-0 rows only (default)");
@@ -1120,7 +1153,7 @@ int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, 
   if ((rc = update_configure())) return rc;
   const BlobLayout L = blob_layout();
   const char* B = (const char*)blob;
-  UpdateWs ws = carve_ws(workspace, (long long)h * w);
+  UpdateWs ws = carve_ws(workspace, h, w);
   ConvArgs a{};
   a.h = h; a.w = w; a.dn_chunk = -1;
   a.src[0] = (const __half*)net; a.src[1] = (const __half*)inp; a.src[2] = (const __half*)dn; a.src[3] = (const __half*)e;

@@ -110,6 +110,32 @@ __device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {
   return r;
 }
 
+// ---- tile-level dependencies between consecutive convs (ConvArgs::flags_in / flags_out) ----
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Whole warp: lanes 0..8 each watch one tile of the 3 x 3 neighbourhood of `tile` (tiles outside the grid count as done).
+// The upstream grid never waits for this one, so the wait always ends; the spin limit only turns a programming error
+// (a flag that is never published) into a trap instead of a hung GPU.
+__device__ __forceinline__ void wait_tiles3x3(const int* flags, int tile, int tiles_x, int n_tiles, int lane) {
+  const int tx = tile % tiles_x, ty = tile / tiles_x, tiles_y = n_tiles / tiles_x;
+  const int nx = tx + lane % 3 - 1, ny = ty + lane / 3 - 1;
+  const bool watch = lane < 9 && nx >= 0 && nx < tiles_x && ny >= 0 && ny < tiles_y;
+  const int* f = flags + (watch ? ny * tiles_x + nx : 0);
+  unsigned spins = 0;
+  while (true) {
+    const int v = watch ? ld_acquire_gpu(f) : 1;
+    if (__all_sync(0xffffffffu, v != 0)) break;
+    __nanosleep(200);
+    if (++spins > (1u << 23)) __trap();
+  }
+}
+
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
   // 1 - 2/(e^{2x}+1): abs error ~1e-7, far below the fp16 rounding that follows; saturates cleanly
@@ -257,7 +283,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 
   // Everything above (barriers, TMEM, delta-head constants) and the weight stream below touch only constants; the
   // activations belong to the previous kernel of the chain: wait for it here (PDL), except in the weight producer.
-  if (warp != TC_W_BPROD) pdl_wait();
+  // With tile flags the roles below wait per tile for the 3 x 3 neighbourhood of the upstream conv instead; everything
+  // else they read was complete before the upstream grid passed its own dependency wait.
+  const bool dep_flags = a.flags_in != nullptr;
+  if (warp != TC_W_BPROD && !dep_flags) pdl_wait();
 
   if (warp >= TC_W_APROD && warp < TC_W_MMA2) {
     // ================= A producers =================
@@ -276,6 +305,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
         const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
         const int c = (ci + rot_chunk) % n_src;
         const int st = seq % C::NA;
+        if (dep_flags && ci == 0 && tile < n_tiles) wait_tiles3x3(a.flags_in, tile, tiles_x, n_tiles, lane);
         pwait(bar_a_empty(st), ((seq / C::NA) & 1) ^ 1, 0);
         const uint32_t dst0 = sA + st * TC_A_BYTES;
         const long long t_fill0 = prof_on ? clock64() : 0;
@@ -326,6 +356,13 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             continue;
           }
           const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
+          if (dep_flags && tile < n_tiles) {      // disp was complete before the upstream conv published anything
+            unsigned spins = 0;
+            while (ld_acquire_gpu(a.flags_in + tile) == 0) {
+              __nanosleep(200);
+              if (++spins > (1u << 23)) __trap();
+            }
+          }
           float dv[DT_PER];                                        // in flight while we wait for the stage
 #pragma unroll
           for (int q = 0; q < DT_PER; ++q) {
@@ -537,6 +574,9 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       if (EPI == EPI_GATES && ok) ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);   // net slice of this thread's r chunk
       if (j == 0) pwait(bar_acc_full(as), (t / C::NACC) & 1, 0);
       tc_fence_after();
+      // z / qx of this tile come from the upstream conv: its flag was observed by the A producers before the MMAs that
+      // just completed; this thread's own acquire makes the data visible to it as well
+      if (EPI == EPI_GRUOUT && dep_flags && tile < n_tiles) (void)ld_acquire_gpu(a.flags_in + tile);
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * N) + j * N;
       float t9[9];
       if (EPI == EPI_DELTA) {
@@ -637,6 +677,11 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 #pragma unroll
         for (int q = 0; q < 9; ++q) a.s9[(p * 2 + chalf) * 9 + q] = t9[q];
       }
+      if (a.flags_out != nullptr) {   // publish the tile: every epilogue thread's stores, then one release store
+        __threadfence();
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        if (tid == 0 && tile < n_tiles) st_release_gpu(a.flags_out + tile, 1);
+      }
       }   // j
     }
   }
@@ -697,6 +742,8 @@ int tc_configure() {
   if ((rc = tc_configure_one<256, EPI_DELTA>())) return rc;
   return CER_OK;
 }
+
+int tc_num_tiles(int h, int w) { return ((w + TC_TW - 1) / TC_TW) * ((h + TC_TH - 1) / TC_TH); }
 
 void tc_set_pair_mode(int gates_mode, int delta_mode) {
   g_pair_modes[0] = gates_mode;

@@ -147,6 +147,12 @@ int cer_set_conv_variant(int variant);
  *   1 = the general block-staged kernels only (any D <= 256 / any radius; CER_LOOKUP=v1). */
 int cer_set_lookup_variant(int variant);
 
+/* Tile-level dependencies between the tensor-core convolutions of a plan iteration (default on; CER_TILE_FLAGS=0):
+ * a conv publishes one flag per finished 16 x 8 tile and the next conv waits for the 3 x 3 tile neighbourhood it reads
+ * instead of for the whole grid, so its CTAs start on the SMs the predecessor's last round leaves idle.  Results are
+ * bit-identical either way. */
+int cer_set_tile_flags(int on);
+
 /* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */
 int cer_debug_set_conv_profile(void* dev_buf);
 
