@@ -119,6 +119,14 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_cta_shared_inc(uint32_t addr) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 // Whole warp: lanes 0..8 each watch one tile of the 3 x 3 neighbourhood of `tile` (tiles outside the grid count as done).
 // The upstream grid never waits for this one, so the wait always ends; the spin limit only turns a programming error
 // (a flag that is never published) into a trap instead of a hung GPU.
@@ -157,9 +165,12 @@ __device__ __forceinline__ void st_half32(__half* dst, const float (&v)[32]) {
     *reinterpret_cast<uint4*>(dst + 8 * q) = pk;
   }
 }
+// Activations are re-written every iteration, and with tile flags a consumer CTA no longer passes a grid-level
+// dependency wait (which is what invalidates L1): read them with ld.global.cg (L2, the coherence point) so a line this
+// SM cached an iteration ago can never be served.  They are streamed once per tile, so L1 had nothing to offer anyway.
 __device__ __forceinline__ void ldg_half32_raw(const __half* src, uint4 (&pk)[4]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) pk[q] = *reinterpret_cast<const uint4*>(src + 8 * q);
+  for (int q = 0; q < 4; ++q) pk[q] = __ldcg(reinterpret_cast<const uint4*>(src + 8 * q));
 }
 __device__ __forceinline__ void unpack_half32(const uint4 (&pk)[4], float (&v)[32]) {
 #pragma unroll
@@ -175,7 +186,7 @@ __device__ __forceinline__ void unpack_half32(const uint4 (&pk)[4], float (&v)[3
 __device__ __forceinline__ void ld_half32(const __half* src, float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint4 pk = *reinterpret_cast<const uint4*>(src + 8 * q);
+    const uint4 pk = __ldcg(reinterpret_cast<const uint4*>(src + 8 * q));
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
     const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&pk.z));
@@ -236,6 +247,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       mbar_init(bar_acc_full(i), kTwoIssuers ? 2 : 1);
       mbar_init(bar_acc_empty(i), CG2 ? 512 : 256);
     }
+    *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM + 8) = 0u;     // epilogue warps that finished a tile (flags_out)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_W_MMA) {
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
           for (int q = 0; q < DT_PER; ++q) {
             const int i = q * TC_DN + dt;
             const int yy = y0 - 4 + i / TC_DT_W, xx = x0 - 4 + i % TC_DT_W;
-            dv[q] = (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) ? __ldg(a.disp + (long long)yy * a.w + xx) : 0.f;
+            dv[q] = (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w) ? __ldcg(a.disp + (long long)yy * a.w + xx) : 0.f;
           }
           pwait(bar_a_empty(st), ((seq / C::NA) & 1) ^ 1, 0);
           const long long t_fill0 = prof_on ? clock64() : 0;
@@ -402,6 +414,24 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       }
     }
   } else if (warp == TC_W_BPROD) {
+    // ================= tile publisher (lane 1): flags_out[tile] = 1 once all 8 epilogue warps have stored the tile ======
+    // (st.release.gpu after an acquire of the warps' release-increments: cumulativity makes every epilogue thread's
+    // stores visible before the flag; the epilogue itself never blocks on the publication)
+    if (lane == 1 && a.flags_out != nullptr) {
+      uint32_t done = 0;
+      for (int t = 0; t < n_iter; ++t) {
+        for (int j = 0; j < MT; ++j) {
+          done += 8;
+          unsigned spins = 0;
+          while (ld_acquire_cta_shared(s0 + C::OFF_TMEM + 8) < done) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();
+          }
+          const int tile = (t * gridDim.x + blockIdx.x) * MT + j;
+          if (tile < n_tiles) st_release_gpu(a.flags_out + tile, 1);
+        }
+      }
+    }
     // ================= B producer =================
     if (lane == 0) {
       const char* wsrc = reinterpret_cast<const char*>(CG2 ? a.wtc2 : a.wtc);
@@ -631,7 +661,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             const float4* q = reinterpret_cast<const float4*>(a.qx + p * 64 + n0);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float4 qq = q[e];
+              const float4 qq = __ldcg(q + e);
               v[4 * e] += qq.x; v[4 * e + 1] += qq.y; v[4 * e + 2] += qq.z; v[4 * e + 3] += qq.w;
             }
 #pragma unroll
@@ -677,10 +707,9 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 #pragma unroll
         for (int q = 0; q < 9; ++q) a.s9[(p * 2 + chalf) * 9 + q] = t9[q];
       }
-      if (a.flags_out != nullptr) {   // publish the tile: every epilogue thread's stores, then one release store
-        __threadfence();
-        asm volatile("bar.sync 5, 256;" ::: "memory");
-        if (tid == 0 && tile < n_tiles) st_release_gpu(a.flags_out + tile, 1);
+      if (a.flags_out != nullptr) {   // this warp's stores of the tile are issued: count it (the publisher thread releases the flag)
+        __syncwarp();
+        if (lane == 0) red_release_cta_shared_inc(s0 + C::OFF_TMEM + 8);
       }
       }   // j
     }
