@@ -127,6 +127,17 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t addr) {
   asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// Whole warp: wait for one tile's flag (lane 0 polls).
+__device__ __forceinline__ void wait_tile_flag(const int* flag, int lane) {
+  if (lane == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_gpu(flag) == 0) {
+      __nanosleep(200);
+      if (++spins > (1u << 23)) __trap();
+    }
+  }
+  __syncwarp();
+}
 // Whole warp: lanes 0..8 each watch one tile of the 3 x 3 neighbourhood of `tile` (tiles outside the grid count as done).
 // The upstream grid never waits for this one, so the wait always ends; the spin limit only turns a programming error
 // (a flag that is never published) into a trap instead of a hung GPU.
@@ -167,10 +178,21 @@ __device__ __forceinline__ void st_half32(__half* dst, const float (&v)[32]) {
 }
 // Activations are re-written every iteration, and with tile flags a consumer CTA no longer passes a grid-level
 // dependency wait (which is what invalidates L1): read them with ld.global.cg (L2, the coherence point) so a line this
-// SM cached an iteration ago can never be served.  They are streamed once per tile, so L1 had nothing to offer anyway.
-__device__ __forceinline__ void ldg_half32_raw(const __half* src, uint4 (&pk)[4]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) pk[q] = __ldcg(reinterpret_cast<const uint4*>(src + 8 * q));
+// SM cached an iteration ago can never be served.  256-bit loads: one request per 32-byte sector, which is what the
+// L1-allocating 128-bit loads amounted to after their sector fill (128-bit .cg loads were measured 10 % slower).
+__device__ __forceinline__ void ldcg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg_half32_raw(const __half* src, uint4 (&pk)[4]) {     // 32 halfs, 64-byte aligned
+  uint32_t a[8], b[8];
+  ldcg256(src, a);
+  ldcg256(src + 16, b);
+  pk[0] = make_uint4(a[0], a[1], a[2], a[3]);
+  pk[1] = make_uint4(a[4], a[5], a[6], a[7]);
+  pk[2] = make_uint4(b[0], b[1], b[2], b[3]);
+  pk[3] = make_uint4(b[4], b[5], b[6], b[7]);
 }
 __device__ __forceinline__ void unpack_half32(const uint4 (&pk)[4], float (&v)[32]) {
 #pragma unroll
@@ -184,15 +206,17 @@ __device__ __forceinline__ void unpack_half32(const uint4 (&pk)[4], float (&v)[3
   }
 }
 __device__ __forceinline__ void ld_half32(const __half* src, float (&v)[32]) {
+  uint4 pk[4];
+  ldg_half32_raw(src, pk);
+  unpack_half32(pk, v);
+}
+__device__ __forceinline__ void ld_float32_add(const float* src, float (&v)[32]) {          // v += 32 floats, 128-byte aligned
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint4 pk = __ldcg(reinterpret_cast<const uint4*>(src + 8 * q));
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&pk.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&pk.w));
-    v[8 * q + 0] = a.x; v[8 * q + 1] = a.y; v[8 * q + 2] = b.x; v[8 * q + 3] = b.y;
-    v[8 * q + 4] = c.x; v[8 * q + 5] = c.y; v[8 * q + 6] = d.x; v[8 * q + 7] = d.y;
+    uint32_t r[8];
+    ldcg256(src + 8 * q, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[8 * q + e] += __uint_as_float(r[e]);
   }
 }
 
@@ -600,13 +624,15 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       const bool ok = yy < a.h && xx < a.w;
       const long long p = ok ? (long long)yy * a.w + xx : 0;
       // operands of the element-wise GRU algebra do not depend on the accumulator: fetch them before waiting for it
+      // With tile flags this grid may have been launched long before its predecessors finished: nothing they (or the
+      // grids before them) wrote may be read until a flag of the upstream conv has been seen -- a published tile
+      // implies that conv passed its own grid-level wait, i.e. every earlier grid of the stream is complete.
+      if (dep_flags && tile < n_tiles) wait_tile_flag(a.flags_in + tile, lane);
       uint4 pre_a[4];
       if (EPI == EPI_GATES && ok) ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);   // net slice of this thread's r chunk
       if (j == 0) pwait(bar_acc_full(as), (t / C::NACC) & 1, 0);
       tc_fence_after();
-      // z / qx of this tile come from the upstream conv: its flag was observed by the A producers before the MMAs that
-      // just completed; this thread's own acquire makes the data visible to it as well
-      if (EPI == EPI_GRUOUT && dep_flags && tile < n_tiles) (void)ld_acquire_gpu(a.flags_in + tile);
+
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (MT * N) + j * N;
       float t9[9];
       if (EPI == EPI_DELTA) {
@@ -658,12 +684,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             float zz[32], nt[32];
             ld_half32(a.z + p * 64 + n0, zz);
             ld_half32(a.net + p * 64 + n0, nt);
-            const float4* q = reinterpret_cast<const float4*>(a.qx + p * 64 + n0);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 qq = __ldcg(q + e);
-              v[4 * e] += qq.x; v[4 * e + 1] += qq.y; v[4 * e + 2] += qq.z; v[4 * e + 3] += qq.w;
-            }
+            ld_float32_add(a.qx + p * 64 + n0, v);
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const float qv = h_round(fast_tanh(h_round(v[e])));
