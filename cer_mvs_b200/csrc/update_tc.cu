@@ -161,19 +161,30 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
 }
 
+// 256-bit stores: one full 32-byte sector per request (a thread owns 64 contiguous bytes of fp16 or 128 of fp32)
+__device__ __forceinline__ void st256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void st_half32(__half* dst, const float (&v)[32]) {
 #pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const __half2 h = __floats2half2_rn(v[16 * q + 2 * e], v[16 * q + 2 * e + 1]);
+      pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    st256(dst + 16 * q, pk);
+  }
+}
+__device__ __forceinline__ void st_float32(float* dst, const float (&v)[32]) {
+#pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 pk;
-    __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
-    __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
-    __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
-    __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-    pk.z = *reinterpret_cast<uint32_t*>(&h2);
-    pk.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(dst + 8 * q) = pk;
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pk[e] = __float_as_uint(v[8 * q + e]);
+    st256(dst + 8 * q, pk);
   }
 }
 // Activations are re-written every iteration, and with tile flags a consumer CTA no longer passes a grid-level
@@ -672,9 +683,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
               st_half32(a.rnet + p * 64 + (n0 - 64), v);
             }
           } else if (ok) {
-            float4* q = reinterpret_cast<float4*>(a.qx + p * 64 + (n0 - 128));
-#pragma unroll
-            for (int e = 0; e < 8; ++e) q[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+            st_float32(a.qx + p * 64 + (n0 - 128), v);
           }
         } else if (EPI == EPI_GRUOUT) {
           if (ok) {

@@ -147,7 +147,8 @@ int cer_set_conv_variant(int variant);
  *   1 = the general block-staged kernels only (any D <= 256 / any radius; CER_LOOKUP=v1). */
 int cer_set_lookup_variant(int variant);
 
-/* Tile-level dependencies between the tensor-core convolutions of a plan iteration (default on; CER_TILE_FLAGS=0):
+/* Tile-level dependencies between the tensor-core convolutions of a plan iteration (opt-in, default off: measured no
+ * faster than grid-level programmatic dependent launch on B200; CER_TILE_FLAGS=1):
  * a conv publishes one flag per finished 16 x 8 tile and the next conv waits for the 3 x 3 tile neighbourhood it reads
  * instead of for the whole grid, so its CTAs start on the SMs the predecessor's last round leaves idle.  Results are
  * bit-identical either way. */

@@ -156,7 +156,7 @@ def test_tile_flag_dependencies_do_not_change_results(cfg):
                     for rep in range(2):                      # the second run re-uses (and must re-zero) the flags
                         outs[(variant, flags, use_graph, rep)] = hp(fm, net, inp, P, Kt, 1.0).clone()
     finally:
-        _lib.lib().cer_set_tile_flags(1)
+        _lib.lib().cer_set_tile_flags(0)
         _lib.lib().cer_set_conv_variant(1)
     for variant in (1, 2):
         ref = outs[(variant, 0, False, 0)]
