@@ -41,6 +41,7 @@ SIGNATURES = {
     "cer_set_conv_variant": (c_int, [c_int]),
     "cer_set_lookup_variant": (c_int, [c_int]),
     "cer_set_tile_flags": (c_int, [c_int]),
+    "cer_set_conv_a_tma": (c_int, [c_int]),
     "cer_debug_set_conv_profile": (c_int, [c_void_p]),
     "cer_gru_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
     "cer_update_blob_bytes": (c_size_t, []),

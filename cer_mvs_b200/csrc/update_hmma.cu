@@ -806,6 +806,7 @@ static int configure_conv() {
   return CER_OK;
 }
 
+void tc_set_a_tma(int on);
 void tc_set_pair_mode(int gates_mode, int delta_mode);   // 0 single CTA, 1 cta_group::2 pairs, 2 multicast pairs, 3 two tiles, 4 3-tap stages
 static int g_variant = -1;
 int conv_variant() {
@@ -1133,6 +1134,11 @@ int cer_set_conv_variant(int variant) {
   g_variant = variant == 0 ? 0 : 1;
   const int m = variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : variant == 5 ? 4 : 0;
   tc_set_pair_mode(variant == 6 ? 1 : m, variant == 5 || variant == 6 ? 0 : m);
+  return CER_OK;
+}
+
+int cer_set_conv_a_tma(int on) {
+  tc_set_a_tma(on);
   return CER_OK;
 }
 

@@ -231,10 +231,19 @@ __device__ __forceinline__ void ld_float32_add(const float* src, float (&v)[32])
   }
 }
 
+// TMA descriptors of the (up to four) NHWC fp16 source tensors, viewed as 4-D (8 channels, x, y, 8 channel groups) so that
+// ONE tensor load of the box (8, 10, 18, 8) writes the whole 18 x 10-pixel halo chunk in the UMMA K-major layout
+// [k-group][halo pixel][8 halfs]; pixels outside the image come back as zeros, which is the conv padding.
+struct alignas(64) TcMaps {
+  CUtensorMap m[4];
+  int use_tma;
+};
+
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int N, int EPI, int MODE>
 __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const ConvArgs a,
-                                                                  const __grid_constant__ CUtensorMap wmap) {
+                                                                  const __grid_constant__ CUtensorMap wmap,
+                                                                  const __grid_constant__ TcMaps amaps) {
   using C = TcCfg<N, MODE>;
   constexpr bool CG2 = C::CG2, MC2 = C::MC2;
   constexpr int MT = C::MT;
@@ -358,6 +367,17 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
         const long long t_fill0 = prof_on ? clock64() : 0;
         if (c == a.dn_chunk) {
           continue;       // generated by the dn warp below; the wait above keeps this warp in step with the ring phases
+        } else if (amaps.use_tma) {
+          // one thread hands the whole chunk to the TMA unit (23 KB, zero-filled outside the image); the other producer
+          // threads only keep the barrier's arrival count
+          if (pt == 0) {
+            mbar_expect_tx(bar_a_full(st), TC_A_BYTES);
+            tma4d(dst0, &amaps.m[c], 0, x0 - 1, y0 - 1, 0, bar_a_full(st));
+          } else {
+            mbar_arrive(bar_a_full(st));
+          }
+          if (prof_on) prof_acc[3] += clock64() - t_fill0;
+          continue;
         } else if (p_hx < TC_HW) {
           // one halo column x one k-group per thread, walking down the 18 halo rows: 2 adds per copy
           const int xx = x0 - 1 + p_hx;
@@ -840,6 +860,62 @@ static int make_weight_map(const void* base, size_t total_bytes, int half_bytes,
   return CER_OK;
 }
 
+// A operand by TMA tensor loads (default) or by 16-byte cp.async from three producer warps (CER_CONV_A=cpasync)
+static int g_a_tma = -1;
+static int a_tma() {
+  if (g_a_tma < 0) {
+    const char* e = getenv("CER_CONV_A");
+    g_a_tma = (e && !strcmp(e, "cpasync")) ? 0 : 1;
+  }
+  return g_a_tma;
+}
+void tc_set_a_tma(int on) { g_a_tma = on ? 1 : 0; }
+
+static int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return CER_ERR_INVALID;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  *out = fn;
+  return CER_OK;
+}
+
+static int make_act_maps(const ConvArgs& a, TcMaps* out) {
+  memset(out, 0, sizeof(*out));
+  out->use_tma = a_tma();
+  if (!out->use_tma) return CER_OK;
+  EncodeTiledFn fn;
+  int rc = get_encode_fn(&fn);
+  if (rc) return rc;
+  for (int c = 0; c < a.n_src; ++c) {
+    if (c == a.dn_chunk) continue;
+    if (!aligned16(a.src[c])) {
+      set_error("conv3x3_tc: source tensor %d is not 16-byte aligned", c);
+      return CER_ERR_INVALID;
+    }
+    // dims, innermost first: 8 channels of a group (16 B) | x | y | the 8 channel groups of a pixel
+    const cuuint64_t gdim[4] = {8, (cuuint64_t)a.w, (cuuint64_t)a.h, 8};
+    const cuuint64_t gstride[3] = {128, (cuuint64_t)a.w * 128, 16};
+    const cuuint32_t box[4] = {8, (cuuint32_t)TC_HW, (cuuint32_t)TC_HH, 8};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&out->m[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(a.src[c]), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (activation halo map) failed (%d)", (int)r);
+      return CER_ERR_INVALID;
+    }
+  }
+  return CER_OK;
+}
+
 template <int N, int EPI, int MODE>
 static int launch_pair(const ConvArgs& a, int tiles, int kind, cudaStream_t stream) {
   CUtensorMap wmap;
@@ -865,7 +941,12 @@ static int launch_pair(const ConvArgs& a, int tiles, int kind, cudaStream_t stre
   cfg.attrs = attr;
   cfg.numAttrs = cer::g_pdl ? 2 : 1;
   if (cer::g_timer) cer::timer_begin(kind, stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<N, EPI, MODE>, a, wmap);
+  TcMaps amaps;
+  {
+    int rc = make_act_maps(a, &amaps);
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<N, EPI, MODE>, a, wmap, amaps);
   if (cer::g_timer) cer::timer_end(stream);
   ++cer::g_launches;
   if (e != cudaSuccess) {
@@ -881,13 +962,18 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = ((a.w + TC_TW - 1) / TC_TW) * ((a.h + TC_TH - 1) / TC_TH);
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
   const int g_pair_mode = N == 192 ? g_pair_modes[0] : N == 256 ? g_pair_modes[1] : TC_SINGLE;
+  TcMaps amaps;
+  {
+    int rc = make_act_maps(a, &amaps);
+    if (rc) return rc;
+  }
   if (N != 64 && tiles >= 2 && g_pair_mode == TC_MT2) {
     constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
     const int units = (tiles + 1) / 2;
     const int grid = units < kNumSMs ? units : kNumSMs;
     CUtensorMap nomap;
     memset(&nomap, 0, sizeof(nomap));
-    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, tc_threads(EPI), (TcCfg<N, M3>::TOTAL), stream, a, nomap);
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, tc_threads(EPI), (TcCfg<N, M3>::TOTAL), stream, a, nomap, amaps);
     return check_launch("conv3x3_tc");
   }
   if (N == 192 && g_pair_mode == TC_S3) {
@@ -895,7 +981,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     CUtensorMap nomap;
     memset(&nomap, 0, sizeof(nomap));
-    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M4>), grid, tc_threads(EPI), (TcCfg<N, M4>::TOTAL), stream, a, nomap);
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M4>), grid, tc_threads(EPI), (TcCfg<N, M4>::TOTAL), stream, a, nomap, amaps);
     return check_launch("conv3x3_tc");
   }
   if (N != 64 && tiles >= 2 && g_pair_mode != TC_SINGLE && g_pair_mode != TC_S3) {
@@ -907,7 +993,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   CUtensorMap nomap;
   memset(&nomap, 0, sizeof(nomap));
   CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, TC_SINGLE>), grid, tc_threads(EPI), (TcCfg<N, TC_SINGLE>::TOTAL), stream, a,
-                 nomap);
+                 nomap, amaps);
   return check_launch("conv3x3_tc");
 }
 

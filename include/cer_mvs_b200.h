@@ -147,6 +147,11 @@ int cer_set_conv_variant(int variant);
  *   1 = the general block-staged kernels only (any D <= 256 / any radius; CER_LOOKUP=v1). */
 int cer_set_lookup_variant(int variant);
 
+/* How the tcgen05 convolutions bring in their activation (A) operand: 1 = one TMA tensor load per 64-channel halo chunk
+ * (4-D view of the NHWC tensor, zero fill outside the image = the conv padding; default), 0 = 16-byte cp.async from the
+ * producer warps (CER_CONV_A=cpasync).  Bit-identical results. */
+int cer_set_conv_a_tma(int on);
+
 /* Tile-level dependencies between the tensor-core convolutions of a plan iteration (opt-in, default off: measured no
  * faster than grid-level programmatic dependent launch on B200; CER_TILE_FLAGS=1):
  * a conv publishes one flag per finished 16 x 8 tile and the next conv waits for the 3 x 3 tile neighbourhood it reads
