@@ -26,15 +26,13 @@ done
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 513 -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --profile-step --warmup 3 > $OUT/${TAG}_launches.log 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:lookup_enc1_v2 -s 96 -c 1 -f -o $OUT/${TAG}_full_lookup64 \
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:lookup_enc1_v3 -s 96 -c 1 -f -o $OUT/${TAG}_full_lookup64 \
     python bench.py --profile-step --warmup 3 > $OUT/${TAG}_full_lookup64.log 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:lookup_enc1_v2 -s 112 -c 1 -f -o $OUT/${TAG}_full_lookup44 \
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:lookup_enc1_v3 -s 112 -c 1 -f -o $OUT/${TAG}_full_lookup44 \
     python bench.py --profile-step --warmup 3 > $OUT/${TAG}_full_lookup44.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:build_volume_h16 -s 6 -c 2 -f -o $OUT/${TAG}_full_build \
     python bench.py --profile-step --warmup 3 > $OUT/${TAG}_full_build.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 384 -c 4 -f -o $OUT/${TAG}_full_convs \
     python bench.py --profile-step --warmup 3 > $OUT/${TAG}_full_convs.log 2>&1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc -s 385 -c 1 -f -o $OUT/${TAG}_full_gates_s3 \
-    python bench.py --profile-step --warmup 3 --conv-variant 5 > $OUT/${TAG}_full_gates_s3.log 2>&1
 fi
 ls -la $OUT | tail -30
