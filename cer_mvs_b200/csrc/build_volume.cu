@@ -282,21 +282,23 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
   // same hypothesis, so a 2-D tile re-uses corner rows in both directions out of L1 (the kernel is bound by L1 misses)
   const int tiles_x = (w + 7) >> 3;
   const int pl = threadIdx.x >> 2;
-  const int x_ = (blockIdx.x % tiles_x) * 8 + (pl & 7), y_ = (blockIdx.x / tiles_x) * 8 + (pl >> 3);
+  // grid = (hypothesis-chunk groups, pixel tiles): the blocks of one pixel tile are scheduled together, so the tile's
+  // source neighbourhoods are pulled into L2 once per stage instead of once per hypothesis range
+  const int x_ = (blockIdx.y % tiles_x) * 8 + (pl & 7), y_ = (blockIdx.y / tiles_x) * 8 + (pl >> 3);
   const bool valid = x_ < w && y_ < h;
   const int x = valid ? x_ : w - 1, y = valid ? y_ : h - 1;
   const long long p = (long long)y * w + x;
   const float xf = (float)x, yf = (float)y;
   const float din = __ldg(disp_in + p);
   const float org = shift ? (din < lo_origin ? lo_origin : din) : din;      // core/corr.py:59-63
-  if (valid && lane == 0 && blockIdx.y == 0) origin_out[p] = org;
+  if (valid && lane == 0 && blockIdx.x == 0) origin_out[p] = org;
 
   const long long img_stride = px * kFeatC;
   int cached_ref = -1;
   Slice16 f1;
   int* grp = sS + (threadIdx.x >> 2) * kGrpWords;
 
-  const int chunk0 = blockIdx.y * kH16Chunks;
+  const int chunk0 = blockIdx.x * kH16Chunks;
   for (int ch = chunk0; ch < chunk0 + kH16Chunks; ++ch) {
     const int d0 = ch * 4;
     if (d0 >= D) break;
@@ -454,7 +456,8 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   const int chunks = ceil_div(D, 8);
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
   if (feats_f16 && build_variant() != 2) {
-    dim3 g16(((w + 7) / 8) * ((h + 7) / 8), ceil_div(ceil_div(D, 4), kH16Chunks));
+    dim3 g16(ceil_div(ceil_div(D, 4), kH16Chunks), ((w + 7) / 8) * ((h + 7) / 8));
+    CER_REQUIRE(g16.y <= 65535u, "cer_build_volume: image too large for the tile grid (%u tiles)", g16.y);
     // corner-dot reuse (opt-in experiment, see build_reuse()): neighbouring hypotheses of the refinement stages fall
     // into neighbouring source cells; the first stage steps several source pixels per hypothesis
     const bool reuse = build_reuse() == 1 || (build_reuse() < 0 && !shift);
