@@ -27,6 +27,9 @@ SIGNATURES = {
     "cer_projection_matrices": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "cer_build_volume": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                  c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p]),
+    "cer_build_volume_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                      c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p]),
     "cer_set_build_variant": (c_int, [c_int]),
     "cer_set_build_reuse": (c_int, [c_int]),
     "cer_pool_pairs": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
@@ -62,6 +65,7 @@ SIGNATURES = {
     "cer_plan_prepare": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_void_p]),
     "cer_plan_build_stage": (c_int, [c_void_p, c_int, c_void_p]),
+    "cer_plan_build_stage_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "cer_plan_partial_volume": (c_void_p, [c_void_p, c_int, C.POINTER(c_size_t)]),
     "cer_plan_iterate_stage": (c_int, [c_void_p, c_int, c_void_p]),
     "cer_plan_finish": (c_int, [c_void_p, c_float, c_void_p, c_void_p]),

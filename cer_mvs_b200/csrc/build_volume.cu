@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
     const __half* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
     const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
     float lo_origin, float* __restrict__ origin_out, float* __restrict__ volume, float out_scale, int per_view,
-    int h, int w) {
+    int h, int w, int y_begin) {
   __shared__ float sP[kMaxPairs][12];
   __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
   // per 4-lane group: 4 samples x {4 byte offsets, 4 weights} = 32 words, padded to 36: a quarter-warp (two groups)
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
   const int pl = threadIdx.x >> 2;
   // grid = (hypothesis-chunk groups, pixel tiles): the blocks of one pixel tile are scheduled together, so the tile's
   // source neighbourhoods are pulled into L2 once per stage instead of once per hypothesis range
-  const int x_ = (blockIdx.y % tiles_x) * 8 + (pl & 7), y_ = (blockIdx.y / tiles_x) * 8 + (pl >> 3);
+  const int x_ = (blockIdx.y % tiles_x) * 8 + (pl & 7), y_ = y_begin + (blockIdx.y / tiles_x) * 8 + (pl >> 3);
   const bool valid = x_ < w && y_ < h;
   const int x = valid ? x_ : w - 1, y = valid ? y_ : h - 1;
   const long long p = (long long)y * w + x;
@@ -440,15 +440,35 @@ extern "C" int cer_set_build_reuse(int mode) {
   return CER_OK;
 }
 
+extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+                                     int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
+                                     float* origin, float* volume, float out_scale, int per_view, int h, int w,
+                                     int y_begin, int y_end, cer_stream_t stream);
+
 extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
                                 int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
                                 float* origin, float* volume, float out_scale, int per_view, int h, int w,
                                 cer_stream_t stream) {
+  return cer_build_volume_rows(feats, feats_f16, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin,
+                               volume, out_scale, per_view, h, w, 0, h, stream);
+}
+
+// Rows [y_begin, y_end) of the volume only (y_begin a multiple of 8): lets a caller that shards views over GPUs
+// all-reduce one band of the partial volume while the next band is being built.
+extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+                                     int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
+                                     float* origin, float* volume, float out_scale, int per_view, int h, int w,
+                                     int y_begin, int y_end, cer_stream_t stream) {
+  CER_REQUIRE(y_begin >= 0 && y_begin < y_end && y_end <= h && (y_begin & 7) == 0,
+              "cer_build_volume_rows: rows [%d, %d) must lie in the image and start on a multiple of 8", y_begin, y_end);
+  const bool whole = y_begin == 0 && y_end == h;
   CER_REQUIRE(feats && Pij && ii && jj && disp_in && origin && volume, "cer_build_volume: null pointer");
   CER_REQUIRE(n_pairs > 0 && n_pairs <= kMaxPairs, "cer_build_volume: n_pairs must be 1..%d", kMaxPairs);
   CER_REQUIRE(D > 0 && h > 0 && w > 0, "cer_build_volume: bad sizes");
   CER_REQUIRE(aligned16(feats), "cer_build_volume: feats must be 16-byte aligned");
   // fp16 features: dot products on tcgen05 (build_volume_tc.cu); a 128-entry tile must span <= 4 pixels
+  CER_REQUIRE(whole || (feats_f16 && build_variant() == 0),
+              "cer_build_volume_rows: row bands are implemented by the FHFMA 4-lane kernel (fp16 features) only");
   if (feats_f16 && D >= 43 && D <= 4096 && build_variant() == 1)
     return build_volume_tc(feats, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale,
                            per_view, h, w, (cudaStream_t)stream);
@@ -456,17 +476,17 @@ extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* P
   const int chunks = ceil_div(D, 8);
   dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
   if (feats_f16 && build_variant() != 2) {
-    dim3 g16(ceil_div(ceil_div(D, 4), kH16Chunks), ((w + 7) / 8) * ((h + 7) / 8));
+    dim3 g16(ceil_div(ceil_div(D, 4), kH16Chunks), ((w + 7) / 8) * ((y_end - y_begin + 7) / 8));
     CER_REQUIRE(g16.y <= 65535u, "cer_build_volume: image too large for the tile grid (%u tiles)", g16.y);
     // corner-dot reuse (opt-in experiment, see build_reuse()): neighbouring hypotheses of the refinement stages fall
     // into neighbouring source cells; the first stage steps several source pixels per hypothesis
     const bool reuse = build_reuse() == 1 || (build_reuse() < 0 && !shift);
     if (reuse)
       CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<true>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
-                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
     else
       CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<false>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
-                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
   } else if (feats_f16)
     CER_LAUNCH(KK_BUILD, build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
                shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);

@@ -239,14 +239,19 @@ int cer_plan_prepare(cer_plan* p, const void* fmaps, int fmaps_f16, const void* 
 }
 
 int cer_plan_build_stage(cer_plan* p, int s, cer_stream_t stream) {
+  CER_REQUIRE(p, "cer_plan_build_stage: null plan");
+  return cer_plan_build_stage_rows(p, s, 0, p->cfg.h, stream);
+}
+
+int cer_plan_build_stage_rows(cer_plan* p, int s, int y_begin, int y_end, cer_stream_t stream) {
   CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_build_stage: bad stage");
   const int D = p->cfg.D[s];
   const double incre = (double)p->cfg.incre[s];
   const float lo = (float)((D / 2) * incre);   // torch.tensor(nIncre // 2 * incre).float(), core/corr.py:60
   cer::g_launches = 0;
-  int rc = cer_build_volume(p->feats, p->cfg.feats_f16, p->Pij + p->vb * 16, p->ii + p->vb, p->jj + p->vb,
-                            p->ve - p->vb, p->disp, s == 0, D, (float)incre, lo, p->origin, p->volume,
-                            1.f / (float)p->n_views, 0, p->cfg.h, p->cfg.w, stream);
+  int rc = cer_build_volume_rows(p->feats, p->cfg.feats_f16, p->Pij + p->vb * 16, p->ii + p->vb, p->jj + p->vb,
+                                 p->ve - p->vb, p->disp, s == 0, D, (float)incre, lo, p->origin, p->volume,
+                                 1.f / (float)p->n_views, 0, p->cfg.h, p->cfg.w, y_begin, y_end, stream);
   p->launches += cer::g_launches;
   return rc;
 }

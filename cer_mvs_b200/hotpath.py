@@ -165,9 +165,10 @@ class DepthHotPath:
     def wait_host(self):
         _lib.check(_lib.lib().cer_plan_wait_host(self._plan), "cer_plan_wait_host")
 
-    def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None):
-        """One depth map over all ranks of ``group``: rank g builds views [g*V/G, (g+1)*V/G), one
-        all-reduce(sum) of the partial mean volume per stage, replicated GRU loop."""
+    def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None, n_bands=4):
+        """One depth map over all ranks of ``group``: rank g builds views [g*V/G, (g+1)*V/G), the partial mean volume of
+        every stage is summed with ``n_bands`` all-reduces (one per band of image rows, each overlapping the build of
+        the next band), replicated GRU loop."""
         import torch.distributed as dist
         from .dist import view_range
         n_views = self._check_maps(fmaps, net, inp)
@@ -186,11 +187,22 @@ class DepthHotPath:
             else:
                 raise RuntimeError("more ranks than source views: use replica mode for the surplus ranks")
             for s in range(len(self.stages)):
-                _lib.check(L.cer_plan_build_stage(self._plan, s, st), "cer_plan_build_stage")
                 n = C.c_size_t()
                 ptr = L.cer_plan_partial_volume(self._plan, s, C.byref(n))
                 vol = torch.as_tensor(_DevView(ptr, n.value), device=self.device)
-                dist.all_reduce(vol, op=dist.ReduceOp.SUM, group=group)
+                D = self.stages[s][0]
+                # band i's all-reduce (NCCL's own stream) overlaps the build of band i+1; bands are
+                # whole 8-row tile rows, the volume is row-major so a band is one contiguous slice
+                rows = -(-self.h1 // max(int(n_bands), 1))
+                rows = max(8, -(-rows // 8) * 8)
+                works = []
+                for y0 in range(0, self.h1, rows):
+                    y1 = min(y0 + rows, self.h1)
+                    _lib.check(L.cer_plan_build_stage_rows(self._plan, s, y0, y1, st), "cer_plan_build_stage_rows")
+                    works.append(dist.all_reduce(vol[y0 * self.w1 * D:y1 * self.w1 * D], op=dist.ReduceOp.SUM,
+                                                 group=group, async_op=True))
+                for wk in works:
+                    wk.wait()
                 _lib.check(L.cer_plan_iterate_stage(self._plan, s, st), "cer_plan_iterate_stage")
             _lib.check(L.cer_plan_finish(self._plan, 1.0 if scale is None else float(scale), out.data_ptr(), st),
                        "cer_plan_finish")

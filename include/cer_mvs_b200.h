@@ -79,6 +79,13 @@ int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const i
 /* Kernel used for fp16 features: 0 = 4-lane gather with 256-bit loads + FHFMA mixed-precision FMA (default),
  * 2 = the same with 8 lanes x 128-bit loads (CER_BUILD=l8), 1 = cp.async gather into UMMA tiles + tcgen05.mma
  * (needs D >= 43; CER_BUILD=tc).  fp32 features always use the 8-lane kernel with plain FFMA. */
+/* The same for image rows [y_begin, y_end) only (y_begin a multiple of 8; fp16 features, default kernel): a caller that
+ * shards source views over GPUs all-reduces one band of the partial volume while the next band is built. */
+int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+                          int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
+                          float* origin, float* volume, float out_scale, int per_view, int h, int w, int y_begin,
+                          int y_end, cer_stream_t stream);
+
 int cer_set_build_variant(int variant);
 
 /* Corner-dot reuse between consecutive hypotheses in the FHFMA build kernel (fp16 features): 0 = never (default:
@@ -239,6 +246,8 @@ int cer_plan_prepare(cer_plan* plan, const void* fmaps, int fmaps_f16, const voi
                      int ctx_f16, const float* poses, const float* intrinsics, int n_views,
                      int view_begin, int view_end, cer_stream_t stream);
 int cer_plan_build_stage(cer_plan* plan, int stage, cer_stream_t stream);
+/* Rows [y_begin, y_end) of the stage's partial volume (see cer_build_volume_rows). */
+int cer_plan_build_stage_rows(cer_plan* plan, int stage, int y_begin, int y_end, cer_stream_t stream);
 float* cer_plan_partial_volume(cer_plan* plan, int stage, size_t* n_floats);
 int cer_plan_iterate_stage(cer_plan* plan, int stage, cer_stream_t stream);
 int cer_plan_finish(cer_plan* plan, float out_scale, float* disp_out, cer_stream_t stream);
