@@ -165,10 +165,12 @@ class DepthHotPath:
     def wait_host(self):
         _lib.check(_lib.lib().cer_plan_wait_host(self._plan), "cer_plan_wait_host")
 
-    def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None, n_bands=4):
+    def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None, n_bands=1):
         """One depth map over all ranks of ``group``: rank g builds views [g*V/G, (g+1)*V/G), the partial mean volume of
         every stage is summed with ``n_bands`` all-reduces (one per band of image rows, each overlapping the build of
-        the next band), replicated GRU loop."""
+        the next band), replicated GRU loop.  Measured on 2 x B200 (cfg 2): 8.05 ms per depth map with one all-reduce
+        per stage, 8.29 ms with four bands -- a 30 MB all-reduce over NVLink costs less than the extra launches, so one
+        band is the default; banding is for slower links / more ranks."""
         import torch.distributed as dist
         from .dist import view_range
         n_views = self._check_maps(fmaps, net, inp)
