@@ -256,7 +256,9 @@ constexpr int kH16Chunks = 4;   // chunks of 4 hypotheses per block in sequence
 // not depend on the hypothesis: the four dots of the previous sample are kept and a corner whose row was already seen
 // is not fetched again (its load is predicated off, so it costs no L1 wavefront -- the limiter of this kernel).  Same
 // operands in the same order, so the result is bit-identical.
-template <bool REUSE>
+// ALL: every lane projects all four samples of its pixel itself (4x redundant arithmetic, no shared-memory slots, no
+// warp barriers): trades ~35 % more instructions for ~23 % fewer L1 wavefronts (cer_set_build_variant(3)).
+template <bool REUSE, bool ALL>
 __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
     const __half* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
     const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
@@ -304,6 +306,9 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
     if (d0 >= D) break;
     const int d = d0 + lane;
     const float dval = __fadd_rn(__fmul_rn((float)(min(d, D - 1) - D / 2), incre), org);   // corr.py:56,66
+    float dvals[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) dvals[s] = __fadd_rn(__fmul_rn((float)(min(d0 + s, D - 1) - D / 2), incre), org);
     float acc = 0.f;
     for (int k = 0; k < n_pairs; ++k) {
       const int ri = sI[k];
@@ -313,34 +318,48 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
       }
       const __half* img2 = feats + sJ[k] * img_stride + lane * 16;
       const float* P = sP[k];
-      const float X0 = fmaf(P[3], dval, fmaf(P[1], yf, P[0] * xf) + P[2]);
-      const float X1 = fmaf(P[7], dval, fmaf(P[5], yf, P[4] * xf) + P[6]);
-      const float X2 = fmaf(P[11], dval, fmaf(P[9], yf, P[8] * xf) + P[10]);
-      float u = __fdiv_rn(X0, X2), v = __fdiv_rn(X1, X2);
-      u = u < -1e4f ? -1e4f : (u > 1e4f ? 1e4f : u);
-      v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
-      const float fu = floorf(u), fv = floorf(v);
-      const float dx = u - fu, dy = v - fv;
-      const int ix = (int)fu, iy = (int)fv;
-      {
+      // X = Pij . (x, y, 1, d), /X2, clamp (corr.py:88), floor; clamped corner offsets (every load legal) and row / column
+      // weights with out-of-range rows / columns zeroed (NaN coordinates keep NaN weights like the reference)
+      const float bx = fmaf(P[1], yf, P[0] * xf) + P[2], by = fmaf(P[5], yf, P[4] * xf) + P[6];
+      const float bz = fmaf(P[9], yf, P[8] * xf) + P[10];
+      auto project = [&](float dv, int4& o4, float4& wt) {
+        const float X0 = fmaf(P[3], dv, bx), X1 = fmaf(P[7], dv, by), X2 = fmaf(P[11], dv, bz);
+        float u = __fdiv_rn(X0, X2), v = __fdiv_rn(X1, X2);
+        u = u < -1e4f ? -1e4f : (u > 1e4f ? 1e4f : u);
+        v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
+        const float fu = floorf(u), fv = floorf(v);
+        const float dx = u - fu, dy = v - fv;
+        const int ix = (int)fu, iy = (int)fv;
         const int y0c = min(max(iy, 0), h - 1), y1c = min(max(iy + 1, 0), h - 1);
         const int x0c = min(max(ix, 0), w - 1), x1c = min(max(ix + 1, 0), w - 1);
-        const float wy0 = (iy >= 0 && iy < h) ? 1.f - dy : ((dy != dy) ? dy : 0.f);
-        const float wy1 = (iy + 1 >= 0 && iy + 1 < h) ? dy : ((dy != dy) ? dy : 0.f);
-        const float wx0 = (ix >= 0 && ix < w) ? 1.f - dx : ((dx != dx) ? dx : 0.f);
-        const float wx1 = (ix + 1 >= 0 && ix + 1 < w) ? dx : ((dx != dx) ? dx : 0.f);
+        wt.x = (iy >= 0 && iy < h) ? 1.f - dy : ((dy != dy) ? dy : 0.f);
+        wt.y = (iy + 1 >= 0 && iy + 1 < h) ? dy : ((dy != dy) ? dy : 0.f);
+        wt.z = (ix >= 0 && ix < w) ? 1.f - dx : ((dx != dx) ? dx : 0.f);
+        wt.w = (ix + 1 >= 0 && ix + 1 < w) ? dx : ((dx != dx) ? dx : 0.f);
+        o4 = make_int4((y0c * w + x0c) * 128, (y0c * w + x1c) * 128, (y1c * w + x0c) * 128, (y1c * w + x1c) * 128);
+      };
+      if (!ALL) {      // the owner lane resolves sample d0 + lane once and publishes it through shared memory
+        int4 o4;
+        float4 wt;
+        project(dval, o4, wt);
         int4* slot = reinterpret_cast<int4*>(grp + lane * 8);
-        slot[0] = make_int4((y0c * w + x0c) * 128, (y0c * w + x1c) * 128, (y1c * w + x0c) * 128, (y1c * w + x1c) * 128);
-        reinterpret_cast<float4*>(slot)[1] = make_float4(wy0, wy1, wx0, wx1);
+        slot[0] = o4;
+        reinterpret_cast<float4*>(slot)[1] = wt;
+        __syncwarp();
       }
-      __syncwarp();
       float part[4];
       int4 po = make_int4(-1, -1, -1, -1);          // corner rows (byte offsets) and dots of the previous sample
       float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        const int4 o4 = *reinterpret_cast<const int4*>(grp + s * 8);
-        const float4 wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
+        int4 o4;
+        float4 wt;
+        if (ALL) {
+          project(dvals[s], o4, wt);
+        } else {
+          o4 = *reinterpret_cast<const int4*>(grp + s * 8);
+          wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
+        }
         float d00, d01, d10, d11;
         if (REUSE) {
           // which corners were seen by the previous sample (uniform over the 4 lanes of a pixel)
@@ -375,7 +394,7 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
         }
         part[s] = ((d00 * wt.x) * wt.z + (d01 * wt.x) * wt.w) + ((d10 * wt.y) * wt.z + (d11 * wt.y) * wt.w);
       }
-      __syncwarp();
+      if (!ALL) __syncwarp();      // the slots are rewritten for the next view
       // butterfly over the 4 lanes: lane L ends with the total of sample L
       float k2[2];
 #pragma unroll
@@ -419,7 +438,7 @@ static int g_build_variant = -1;
 static int build_variant() {
   if (g_build_variant < 0) {
     const char* e = getenv("CER_BUILD");
-    g_build_variant = (e && !strcmp(e, "tc")) ? 1 : (e && !strcmp(e, "l8")) ? 2 : 0;
+    g_build_variant = (e && !strcmp(e, "tc")) ? 1 : (e && !strcmp(e, "l8")) ? 2 : (e && !strcmp(e, "noslots")) ? 3 : 0;
   }
   return g_build_variant;
 }
@@ -428,8 +447,9 @@ static int build_variant() {
 using namespace cer;
 
 extern "C" int cer_set_build_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 2,
-              "cer_set_build_variant: 0 FHFMA gather, 4 lanes x 256-bit loads (default); 1 tcgen05 gather; 2 FHFMA gather, 8 lanes");
+  CER_REQUIRE(variant >= 0 && variant <= 3,
+              "cer_set_build_variant: 0 FHFMA gather, 4 lanes x 256-bit loads (default); 1 tcgen05 gather; 2 FHFMA gather, "
+              "8 lanes; 3 FHFMA gather, 4 lanes, every lane projects its pixel's samples itself (no shared-memory slots)");
   g_build_variant = variant;
   return CER_OK;
 }
@@ -467,7 +487,7 @@ extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const flo
   CER_REQUIRE(D > 0 && h > 0 && w > 0, "cer_build_volume: bad sizes");
   CER_REQUIRE(aligned16(feats), "cer_build_volume: feats must be 16-byte aligned");
   // fp16 features: dot products on tcgen05 (build_volume_tc.cu); a 128-entry tile must span <= 4 pixels
-  CER_REQUIRE(whole || (feats_f16 && build_variant() == 0),
+  CER_REQUIRE(whole || (feats_f16 && (build_variant() == 0 || build_variant() == 3)),
               "cer_build_volume_rows: row bands are implemented by the FHFMA 4-lane kernel (fp16 features) only");
   if (feats_f16 && D >= 43 && D <= 4096 && build_variant() == 1)
     return build_volume_tc(feats, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale,
@@ -482,11 +502,14 @@ extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const flo
     // into neighbouring source cells; the first stage steps several source pixels per hypothesis
     const bool reuse = build_reuse() == 1 || (build_reuse() < 0 && !shift);
     if (reuse)
-      CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<true>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
+      CER_LAUNCH(KK_BUILD, (build_volume_h16_kernel<true, false>), g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
                  disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
+    else if (build_variant() == 3)
+      CER_LAUNCH(KK_BUILD, (build_volume_h16_kernel<false, true>), g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj,
+                 n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
     else
-      CER_LAUNCH(KK_BUILD, build_volume_h16_kernel<false>, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
-                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
+      CER_LAUNCH(KK_BUILD, (build_volume_h16_kernel<false, false>), g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj,
+                 n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
   } else if (feats_f16)
     CER_LAUNCH(KK_BUILD, build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
                shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);

@@ -11,11 +11,11 @@ from util import H, V, W, h1, t, w1
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["fhfma", "fhfma_8lane", "tcgen05"], autouse=True)
+@pytest.fixture(params=["fhfma", "fhfma_noslots", "fhfma_8lane", "tcgen05"], autouse=True)
 def build_variant(request):
     """fp16-feature builds run on both kernels: FHFMA gather (default) and the tcgen05 gather."""
     from cer_mvs_b200 import _lib
-    _lib.check(_lib.lib().cer_set_build_variant({"fhfma": 0, "fhfma_8lane": 2, "tcgen05": 1}[request.param]))
+    _lib.check(_lib.lib().cer_set_build_variant({"fhfma": 0, "fhfma_noslots": 3, "fhfma_8lane": 2, "tcgen05": 1}[request.param]))
     yield request.param
     _lib.lib().cer_set_build_variant(0)
 STAGES = [(64, 0.0025 / 64, True), (44, 0.0025 / 320, False)]
