@@ -133,6 +133,40 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TS* __restrict_
   }
 }
 
+
+// fp16 -> fp16, 64 channels (the feature / context maps of the plan): 32 pixels x 64 channels per block, 16-byte loads
+// along the pixel axis of every channel plane, 16-byte stores that cover whole 128-byte NHWC pixels (512 contiguous
+// bytes per warp store).  `scale` is applied exactly like the general kernel (float multiply, round to fp16).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_c64_h16_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                                  long long px, float scale) {
+  constexpr int kPitch = 72;                       // halfs per pixel row of the tile (144 B: 16-byte aligned rows)
+  __shared__ __align__(16) __half tile[32 * kPitch];
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const __half* s = src + (long long)n * 64 * px;
+  __half* d = dst + (long long)n * 64 * px;
+  const int t = threadIdx.x;
+  {
+    const int c = t >> 2, q = t & 3;               // channel, group of 8 pixels
+    const long long p = p0 + 8 * q;
+    __align__(16) __half v[8];
+    if (p + 8 <= px) {
+      *reinterpret_cast<uint4*>(v) = __ldcs(reinterpret_cast<const uint4*>(s + (long long)c * px + p));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (p + i < px) ? s[(long long)c * px + p + i] : __float2half_rn(0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[(8 * q + i) * kPitch + c] = __float2half_rn(__half2float(v[i]) * scale);
+  }
+  __syncthreads();
+  {
+    const int pl = t >> 3, ch = t & 7;             // pixel of the tile, group of 8 channels
+    if (p0 + pl < px)
+      *reinterpret_cast<uint4*>(d + (p0 + pl) * 64 + ch * 8) = *reinterpret_cast<const uint4*>(tile + pl * kPitch + ch * 8);
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const TS* __restrict__ src, TD* __restrict__ dst,
                                                           int C, long long px) {
@@ -371,6 +405,11 @@ int cer_nchw_to_nhwc_pad(const void* src, int src_f16, void* dst, int dst_f16, i
   CER_REQUIRE(src && dst && n > 0 && C > 0 && dstC >= C && h > 0 && w > 0, "cer_nchw_to_nhwc: bad arguments");
   const long long px = (long long)h * w;
   dim3 grid(ceil_div(px, 32), ceil_div(dstC, 32), n);
+  if (src_f16 && dst_f16 && C == 64 && dstC == 64 && (px % 8) == 0 && aligned16(src) && aligned16(dst) && n <= 65535) {
+    CER_LAUNCH(KK_LAYOUT, nchw_to_nhwc_c64_h16_kernel, dim3(ceil_div(px, 32), n), 256, 0, stream, (const __half*)src,
+               (__half*)dst, px, scale);
+    return check_launch("cer_nchw_to_nhwc");
+  }
   if (src_f16 && dst_f16)
     CER_LAUNCH(KK_LAYOUT, (nchw_to_nhwc_kernel<__half, __half>), grid, 256, 0, stream, (const __half*)src, (__half*)dst, C, dstC, px, scale);
   else if (src_f16 && !dst_f16)

@@ -169,3 +169,18 @@ def test_identity_view_known_answer():
     want = (f[0, 0] ** 2).sum(0).reshape(-1, 1) / 64
     got = cb.volume[0].cpu()
     torch.testing.assert_close(got, want.expand_as(got), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("hw", [(20, 28), (37, 53), (296, 400)])
+def test_layout_kernels_match_permute(hw, build_variant):
+    """NCHW -> NHWC (x 1/8) in fp16: the 64-channel fast path (px % 8 == 0) and the general kernel against torch."""
+    if build_variant != "fhfma":
+        pytest.skip("independent of the build kernel")
+    from cer_mvs_b200 import _lib
+    h, w = hw
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(3, 64, h, w, generator=g, device="cuda").half()
+    out = torch.empty(3, h, w, 64, device="cuda", dtype=torch.float16)
+    _lib.check(_lib.lib().cer_nchw_to_nhwc(x.data_ptr(), 1, out.data_ptr(), 1, 3, 64, h, w, 0.125, _lib.stream_ptr()))
+    want = (x.float() * 0.125).half().permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(out, want)
