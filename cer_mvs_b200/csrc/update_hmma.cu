@@ -259,7 +259,7 @@ static size_t lookup_enc1_smem(int D) {
 // KA v2 (plan, D = 64 / 44): the same fused step, restructured around what bounded v1 (ncu: issue slots 37 %, warps
 // stalled on block barriers and on the dependent load -> tap -> MMA phases, 800 instructions per warp):
 //   * warp-autonomous: each warp owns 32 consecutive pixels (8 KB of contiguous volume rows) end to end; the only
-//     block barrier is the one after the constant 1x1 weights, before the dependency wait.  Warps of a CTA and CTAs
+//     block barrier is the one that publishes the shared 1x1 weights, right before the MMA.  Warps of a CTA and CTAs
 //     of an SM drift into different phases, so row loads of one overlap the tap arithmetic of another.
 //   * every load of the chunk (16 x 16-byte row loads per lane, disparity, origin, 18 delta partials) is issued
 //     before the first use: one latency exposure per chunk instead of three.

@@ -1,22 +1,25 @@
 // UpdateBlock 3x3 convolutions, v3: implicit GEMM on tcgen05.mma (5th-gen tensor cores), accumulators
 // in TMEM.  Same math, inputs, outputs and fused epilogues as update_hmma.cu.
 //
-// Persistent CTAs (one per SM) walk over 16 x 8 pixel tiles (M = 128), N = 64 / 192 / 256 output
-// channels, K = n_src x 9 taps x 64 channels; the TMEM accumulator is double-buffered so the epilogue
-// of tile t overlaps the MMAs of tile t+1.  Warp roles (256 threads):
+// Persistent CTAs (one per SM; the two wide convs as cta_group::2 CTA pairs by default) walk over 16 x 8 pixel tiles
+// (M = 128 per CTA), N = 64 / 192 / 256 output channels, K = n_src x 9 taps x 64 channels; the TMEM accumulator is
+// double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1.  Warp roles (512 threads for the gate conv,
+// 416 for the others):
 //
-//   warps 0-3  epilogue: tcgen05.ld gives every thread all N channels of one pixel (TMEM lane = pixel);
-//              bias / sigmoid / tanh / GRU blend / delta dots, NHWC stores; then releases the accumulator.
-//   warp 4     MMA issuer: one elected lane, 4 (k16) tcgen05.mma per (chunk, tap); tcgen05.commit hands
-//              smem stages back to the producers and accumulators to the epilogue.  Owns the TMEM allocation.
-//   warp 5     B producer: one elected lane streams the pre-tiled weights of each (chunk, tap) with
-//              cp.async.bulk (TMA 1-D) into a ring; for N = 64 all 9 taps stay resident for the whole kernel.
-//   warps 6-7  A producers: per 64-channel chunk the 18 x 10 halo tile is brought in with 16-byte cp.async
-//              (zero fill outside the image = the conv padding) in the UMMA K-major no-swizzle layout
-//              [k-group 8][halo pixel 180][8 halfs]; a 3x3 tap is then just a shifted start address of the
-//              same tile (LBO = 180*16 B between k-groups, SBO = 10*16 B between image rows = 8-row
-//              core-matrix groups).  The disparity-encoder chunk of the gate conv (core/update.py:80-85,97)
-//              is computed here straight from disp instead of being read from HBM.
+//   warps 0-7    epilogue: tcgen05.ld gives every thread 32 channels of one pixel (TMEM lane = pixel; warps w and w+4
+//                split the columns); bias / sigmoid / tanh / GRU blend / delta dots, 256-bit NHWC loads and stores;
+//                then releases the accumulator.
+//   warp 8       MMA issuer: one elected lane, 4 (k16) tcgen05.mma per (chunk, tap); tcgen05.commit hands smem stages
+//                back to the producers and accumulators to the epilogue.  Owns the TMEM allocation.
+//   warp 9       B producer: lane 0 streams the pre-tiled weights with cp.async.bulk / TMA into an mbarrier ring (N = 64
+//                and the paired delta conv keep all 9 taps resident); lane 1 publishes tile flags when they are enabled.
+//   warps 10-12  A producers: per 64-channel chunk ONE 4-D TMA tensor load brings the 18 x 10 halo tile in (zero fill
+//                outside the image = the conv padding) in the UMMA K-major no-swizzle layout
+//                [k-group 8][halo pixel 180][8 halfs]; a 3x3 tap is then just a shifted start address of the same tile
+//                (LBO = 180*16 B between k-groups, SBO = 10*16 B between image rows = 8-row core-matrix groups).
+//                (cer_set_conv_a_tma(0): the same tile by 16-byte cp.async from these three warps.)
+//   warps 13-15  gate conv only: the disparity-encoder chunk (core/update.py:80-85,97) is computed straight from disp
+//                into the A ring instead of being read from HBM.
 #include <string.h>
 
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
