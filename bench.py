@@ -339,6 +339,8 @@ def run_ours(args):
                        "design_frac": moved_b / (us * 1e-6) / 1e9 / pk["hbm"],
                        "note": "rows are read whole (4D+8 B in, 132 B out per pixel-slot = 396 B at D=64), so 284 "
                                "algorithmic bytes cap 'frac' at 0.72 of the achieved HBM fraction ('design_frac')"}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes of this launch from the ncu capture
+        lookup_roof["traffic"] = json.load(open(tpath)).get("lookup_dropin_slotsV") if os.path.isfile(tpath) else None
         del vol, lout
 
     # ---- view-sharded single image (NCCL all-reduce of the partial volume per stage) ----
