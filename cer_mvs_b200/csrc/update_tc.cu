@@ -698,12 +698,19 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             for (int e = 0; e < 32; ++e) v[e] = fast_sigmoid(h_round(v[e]));
             if (ok) st_half32(a.z + p * 64 + n0, v);
           } else if (n0 < 128) {
-            if (ok) {
-              float nt[32];
-              unpack_half32(pre_a, nt);          // n0 - 64 == chalf * 32
+            if (ok) {      // fp16(fp16(sigmoid(fp16(convr))) * net): the product of two fp16 values rounded once = HMUL2
+              const __half2* n2 = reinterpret_cast<const __half2*>(pre_a);          // n0 - 64 == chalf * 32
+              uint32_t outp[16];
 #pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = h_round(fast_sigmoid(h_round(v[e]))) * nt[e];
-              st_half32(a.rnet + p * 64 + (n0 - 64), v);
+              for (int e2 = 0; e2 < 16; ++e2) {
+                const float2 af = __half22float2(__floats2half2_rn(v[2 * e2], v[2 * e2 + 1]));
+                const __half2 o = __hmul2(__floats2half2_rn(fast_sigmoid(af.x), fast_sigmoid(af.y)), n2[e2]);
+                outp[e2] = *reinterpret_cast<const uint32_t*>(&o);
+              }
+              const uint32_t(&lo)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&outp[0]);
+              const uint32_t(&hi)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&outp[8]);
+              st256(a.rnet + p * 64 + (n0 - 64), lo);
+              st256(a.rnet + p * 64 + (n0 - 64) + 16, hi);
             }
           } else if (ok) {
             st_float32(a.qx + p * 64 + (n0 - 128), v);
@@ -713,16 +720,33 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             // (prefetching z / net / qx before the accumulator wait was measured slower: 39 vs 36 us -- ptxas holds this
             // kernel at 128 registers, the extra 64 live registers spill, and the loads are L2 hits that the eight
             // epilogue warps already overlap)
-            float zz[32], nt[32];
-            ld_half32(a.z + p * 64 + n0, zz);
-            ld_half32(a.net + p * 64 + n0, nt);
+            // The element-wise GRU algebra on packed fp16 pairs: autocast rounds every op to fp16, and for fp16 operands
+            // HSUB2(1, z) and HMUL2 are exactly fp16(float op) (1 - z and the products are exact in fp32); the final sum
+            // is done in fp32 and rounded once, like torch's opmath path.  ~35 % fewer epilogue instructions than the
+            // unpack-to-float version (the q conv is bound by its epilogue's issue slots, not by its MMAs).
+            uint4 zk[4], nk[4];
+            ldg_half32_raw(a.z + p * 64 + n0, zk);
+            ldg_half32_raw(a.net + p * 64 + n0, nk);
             ld_float32_add(a.qx + p * 64 + n0, v);
+            const __half2* z2 = reinterpret_cast<const __half2*>(zk);
+            const __half2* n2 = reinterpret_cast<const __half2*>(nk);
+            const __half2 one2 = __floats2half2_rn(1.f, 1.f);
+            uint32_t outp[16];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float qv = h_round(fast_tanh(h_round(v[e])));
-              v[e] = h_round(h_round(h_round(1.f - zz[e]) * nt[e]) + h_round(zz[e] * qv));
+            for (int e2 = 0; e2 < 16; ++e2) {
+              const float2 af = __half22float2(__floats2half2_rn(v[2 * e2], v[2 * e2 + 1]));        // fp16(convq)
+              const __half2 q = __floats2half2_rn(fast_tanh(af.x), fast_tanh(af.y));                  // fp16(tanh)
+              const float2 f1 = __half22float2(__hmul2(__hsub2(one2, z2[e2]), n2[e2]));              // fp16(fp16(1-z)*net)
+              const float2 f2 = __half22float2(__hmul2(z2[e2], q));                                   // fp16(z*q)
+              const __half2 o = __floats2half2_rn(f1.x + f2.x, f1.y + f2.y);
+              outp[e2] = *reinterpret_cast<const uint32_t*>(&o);
             }
-            st_half32(a.net + p * 64 + n0, v);
+            {
+              const uint32_t(&lo)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&outp[0]);
+              const uint32_t(&hi)[8] = *reinterpret_cast<const uint32_t(*)[8]>(&outp[8]);
+              st256(a.net + p * 64 + n0, lo);
+              st256(a.net + p * 64 + n0 + 16, hi);
+            }
           }
         } else {  // EPI_DELTA
           // relu(fp16(acc + bias)) stays packed in fp16; the 9-tap dot with the (fp16) delta.2 weights runs on the
