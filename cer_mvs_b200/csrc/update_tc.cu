@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
         }
         if (EPI == EPI_RELU) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaxf(h_round(v[e]), 0.f);
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);     // relu commutes with the (monotone) fp16 rounding of st_half32
           if (ok) st_half32(a.out_h + p * 64 + n0, v);
         } else if (EPI == EPI_GATES) {
           if (n0 < 64) {
