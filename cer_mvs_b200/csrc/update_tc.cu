@@ -92,7 +92,7 @@ struct TcCfg {
   static constexpr int TMEM_COLS = (NACC * MT * N <= 128) ? 128 : (NACC * MT * N <= 256 ? 256 : 512);
   static constexpr int OFF_B = NA * TC_A_BYTES;
   static constexpr int OFF_EXTRA = OFF_B + NB * STAGE_BYTES;                  // DELTA: bias [256] f32 + w2 [9][256] f16; GATES: disparity tile
-  static constexpr int EXTRA_BYTES = (N == 256) ? 256 * 4 + 9 * 256 * 2 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
+  static constexpr int EXTRA_BYTES = (N == 256) ? 256 * 4 + 9 * (256 + 8) * 2 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
   static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
   static constexpr int NUM_BAR = 2 * NA + 3 * NB + 2 * NACC;  // a_full/empty, b_full/empty/peer_full, acc_full/empty
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
@@ -157,6 +157,25 @@ __device__ __forceinline__ void wait_tiles3x3(const int* flags, int tile, int ti
     if (++spins > (1u << 23)) __trap();
   }
 }
+
+// tcgen05.ld 16x256b.x2: 16 TMEM lanes (rows) x 16 fp32 columns, delivered per 8-column block in the mma.sync m16n8
+// accumulator layout (lane = 4 g + q: r0,r1 = row g, cols 2q,2q+1; r2,r3 = row g+8; r4..r7 = the same for cols +8), which
+// after packing to fp16 pairs IS the m16n8k16 A fragment (a0 = r0:r1, a1 = r2:r3, a2 = r4:r5, a3 = r6:r7).
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void mma16816_f32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// Delta head (second delta conv as 9 per-pixel dots over 256 channels): 1 = on mma.sync straight from the TMEM
+// accumulator fragments (32 HMMA per warp and tile), 0 = 288 FHFMA per thread and 32-channel block (the round's earlier
+// form, kept for A/B: the delta conv was bound by this epilogue's issue slots, not by its MMAs).
+constexpr int kDeltaHeadMma = 1;
+constexpr int kW2Pitch = 256 + 8;      // halfs per tap row of the delta.2 weights in shared memory (conflict-free B fragments)
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
     float* exb = reinterpret_cast<float*>(smem + C::OFF_EXTRA);
     __half* exw = reinterpret_cast<__half*>(smem + C::OFF_EXTRA + 256 * 4);
     for (int i = tid; i < 256; i += 256) exb[i] = __ldg(a.bias + i);
-    for (int i = tid; i < 9 * 256; i += 256) exw[i] = __float2half_rn(__ldg(a.w2 + i));
+    for (int i = tid; i < 9 * 256; i += 256) exw[(i >> 8) * kW2Pitch + (i & 255)] = __float2half_rn(__ldg(a.w2 + i));
   }
   tc_fence_before();
   __syncthreads();
@@ -673,6 +692,68 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 #pragma unroll
         for (int q = 0; q < 9; ++q) t9[q] = 0.f;
       }
+      if (EPI == EPI_DELTA && kDeltaHeadMma) {
+        // relu(fp16(acc + bias)) -> fp16 A fragments -> mma.sync against the delta.2 weights (taps 0..7 = n-tile 0, tap 8
+        // = column 0 of n-tile 1): this warp's 32 pixels (two m16 tiles) x its 128 channels (8 k16 steps)
+        const float* exb = reinterpret_cast<const float*>(smem + C::OFF_EXTRA);
+        const __half* exw = reinterpret_cast<const __half*>(smem + C::OFF_EXTRA + 256 * 4);
+        const int g = lane >> 2, q4 = lane & 3;
+        const __half2 hzero = __floats2half2_rn(0.f, 0.f);
+        float d0[2][4], d1[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) d0[mt][e] = d1[mt][e] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < 8; ++ks) {
+          const int c0 = chalf * 128 + ks * 16;
+          uint32_t r0[8], r1[8];
+          tc_ld_16x256b_x2(lane_addr + c0, r0);
+          tc_ld_16x256b_x2(lane_addr + (16u << 16) + c0, r1);
+          const uint32_t b00 = *reinterpret_cast<const uint32_t*>(exw + g * kW2Pitch + c0 + 2 * q4);
+          const uint32_t b01 = *reinterpret_cast<const uint32_t*>(exw + g * kW2Pitch + c0 + 8 + 2 * q4);
+          const uint32_t b10 = g == 0 ? *reinterpret_cast<const uint32_t*>(exw + 8 * kW2Pitch + c0 + 2 * q4) : 0u;
+          const uint32_t b11 = g == 0 ? *reinterpret_cast<const uint32_t*>(exw + 8 * kW2Pitch + c0 + 8 + 2 * q4) : 0u;
+          const float2 bb0 = *reinterpret_cast<const float2*>(exb + c0 + 2 * q4);
+          const float2 bb1 = *reinterpret_cast<const float2*>(exb + c0 + 8 + 2 * q4);
+          tc_ld_wait();
+          auto frag = [&](const uint32_t (&r)[8], uint32_t (&af)[4]) {
+            const __half2 h0 = __hmax2(__floats2half2_rn(__uint_as_float(r[0]) + bb0.x, __uint_as_float(r[1]) + bb0.y), hzero);
+            const __half2 h1 = __hmax2(__floats2half2_rn(__uint_as_float(r[2]) + bb0.x, __uint_as_float(r[3]) + bb0.y), hzero);
+            const __half2 h2 = __hmax2(__floats2half2_rn(__uint_as_float(r[4]) + bb1.x, __uint_as_float(r[5]) + bb1.y), hzero);
+            const __half2 h3 = __hmax2(__floats2half2_rn(__uint_as_float(r[6]) + bb1.x, __uint_as_float(r[7]) + bb1.y), hzero);
+            af[0] = *reinterpret_cast<const uint32_t*>(&h0);
+            af[1] = *reinterpret_cast<const uint32_t*>(&h1);
+            af[2] = *reinterpret_cast<const uint32_t*>(&h2);
+            af[3] = *reinterpret_cast<const uint32_t*>(&h3);
+          };
+          uint32_t a0[4], a1[4];
+          frag(r0, a0);
+          frag(r1, a1);
+          mma16816_f32(d0[0], a0, b00, b01);
+          mma16816_f32(d1[0], a0, b10, b11);
+          mma16816_f32(d0[1], a1, b00, b01);
+          mma16816_f32(d1[1], a1, b10, b11);
+        }
+        if (j == MT - 1) {
+          tc_fence_before();
+          arrive_leader(bar_acc_empty(as));           // accumulator stage may be overwritten
+        }
+        // accumulator fragment (row g / g+8 of m-tile mt, taps 2q, 2q+1; tap 8 in column 0 of the second n-tile)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int mm = quad * 32 + mt * 16 + g + 8 * hf;
+            const int y2 = y0 + (mm >> 3), x2 = x0 + (mm & 7);
+            if (y2 < a.h && x2 < a.w) {
+              float* dst = a.s9 + (((long long)y2 * a.w + x2) * 2 + chalf) * 9;
+              dst[2 * q4] = d0[mt][2 * hf];
+              dst[2 * q4 + 1] = d0[mt][2 * hf + 1];
+              if (q4 == 0) dst[8] = d1[mt][2 * hf];
+            }
+          }
+      } else {
 #pragma unroll 1
       for (int cb = chalf * (N / 64); cb < (chalf + 1) * (N / 64); ++cb) {
         uint32_t raw[32];
@@ -766,7 +847,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             float acc = t9[q];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const uint4 w = *reinterpret_cast<const uint4*>(exw + q * 256 + n0 + 8 * j4);
+              const uint4 w = *reinterpret_cast<const uint4*>(exw + q * kW2Pitch + n0 + 8 * j4);
               acc = fhfma_lo(hv[4 * j4 + 0], w.x, acc); acc = fhfma_hi(hv[4 * j4 + 0], w.x, acc);
               acc = fhfma_lo(hv[4 * j4 + 1], w.y, acc); acc = fhfma_hi(hv[4 * j4 + 1], w.y, acc);
               acc = fhfma_lo(hv[4 * j4 + 2], w.z, acc); acc = fhfma_hi(hv[4 * j4 + 2], w.z, acc);
@@ -784,6 +865,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 #pragma unroll
         for (int q = 0; q < 9; ++q) a.s9[(p * 2 + chalf) * 9 + q] = t9[q];
       }
+      }   // generic (per-pixel) epilogue
       if (a.flags_out != nullptr) {   // this warp's stores of the tile are issued: count it (the publisher thread releases the flag)
         __syncwarp();
         if (lane == 0) red_release_cta_shared_inc(s0 + C::OFF_TMEM + 8);
