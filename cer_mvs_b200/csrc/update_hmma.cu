@@ -1127,13 +1127,14 @@ int cer_debug_set_conv_profile(void* dev_buf) {
 }
 
 int cer_set_conv_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 6,
-              "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs (default), 2 tcgen05 one tile per CTA, "
+  CER_REQUIRE(variant >= 0 && variant <= 7,
+              "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs for both wide convs, 2 tcgen05 one tile per CTA, "
               "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA, 5 tcgen05 one tile per CTA with 3-tap weight stages, "
-              "6 cta_group::2 pairs for the gate conv + one tile per CTA for the delta conv");
+              "6 cta_group::2 pairs for the gate conv + one tile per CTA for the delta conv (default), "
+              "7 pairs for the gate conv + two tiles per CTA for the delta conv");
   g_variant = variant == 0 ? 0 : 1;
   const int m = variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : variant == 5 ? 4 : 0;
-  tc_set_pair_mode(variant == 6 ? 1 : m, variant == 5 || variant == 6 ? 0 : m);
+  tc_set_pair_mode(variant >= 6 ? 1 : m, variant == 7 ? 3 : (variant == 5 || variant == 6) ? 0 : m);
   return CER_OK;
 }
 

@@ -899,8 +899,9 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 // ---- host ----------------------------------------------------------------------------------------
 // Pair modes apply to the N = 192 / 256 convs (weights streamed per tile); the N = 64 convs keep their weights resident.
 // Mode of the streamed-weight convs (A/B switch), per kernel: [0] gate conv (N = 192), [1] delta conv (N = 256).
-// Measured default: CTA pairs for both (gate conv 90 vs 101 us; delta conv with resident half weight sets 48 vs 52 us).
-static int g_pair_modes[2] = {TC_CG2, TC_CG2};
+// Measured default: CTA pairs for the gate conv (79 vs 84 us); the delta conv as single CTAs (43 us; as a pair with
+// resident half weight sets its M256 x N256 MMAs run at ~200 instead of 128 cycles: 48 us).
+static int g_pair_modes[2] = {TC_CG2, TC_SINGLE};
 
 template <int N, int EPI>
 static int tc_configure_one() {

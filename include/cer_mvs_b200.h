@@ -135,10 +135,10 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     cer_stream_t stream);
 
 /* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on all of them):
- *   1 = default (CER_CONV unset or tc2): tcgen05.mma + TMEM, persistent CTAs; the two wide convs as CTA pairs issuing
- *       cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile; the delta conv keeps its half weight
- *       set resident), the N = 64 convs one 128-pixel tile per CTA with resident weights
- *   6 = CTA pairs for the gate conv only, the delta conv one tile per CTA
+ *   6 = default (CER_CONV unset): tcgen05.mma + TMEM, persistent CTAs; the gate conv (N = 192) as CTA pairs issuing
+ *       cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), every other conv one 128-pixel tile per CTA
+ *   1 = both wide convs as cta_group::2 pairs, the delta conv with its half weight set resident (CER_CONV=tc2)
+ *   7 = pairs for the gate conv, two tiles per CTA for the delta conv
  *   2 = every conv one 128-pixel tile per CTA at a time (CER_CONV=tc1)
  *   3 = the N >= 192 convolutions as 2-CTA clusters that multicast each weight tile
  *   4 = the N >= 192 convolutions with two 128-pixel tiles per CTA sharing each weight stage

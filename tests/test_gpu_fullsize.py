@@ -146,7 +146,7 @@ def test_tile_flag_dependencies_do_not_change_results(cfg):
     P, Kt = torch.from_numpy(poses)[None].cuda(), torch.from_numpy(K)[None].cuda()
     outs = {}
     try:
-        for variant in (1, 2):
+        for variant in (6, 1, 2):
             _lib.check(_lib.lib().cer_set_conv_variant(variant))
             for flags in (0, 1):
                 _lib.check(_lib.lib().cer_set_tile_flags(flags))
@@ -157,8 +157,8 @@ def test_tile_flag_dependencies_do_not_change_results(cfg):
                         outs[(variant, flags, use_graph, rep)] = hp(fm, net, inp, P, Kt, 1.0).clone()
     finally:
         _lib.lib().cer_set_tile_flags(0)
-        _lib.lib().cer_set_conv_variant(1)
-    for variant in (1, 2):
+        _lib.lib().cer_set_conv_variant(6)
+    for variant in (6, 1, 2):
         ref = outs[(variant, 0, False, 0)]
         assert torch.isfinite(ref).all()
         for k, o in outs.items():
@@ -183,7 +183,7 @@ def test_conv_a_operand_tma_equals_cpasync(grid):
     P, Kt = torch.from_numpy(poses)[None].cuda(), torch.from_numpy(K)[None].cuda()
     outs = {}
     try:
-        for variant in (1, 2):
+        for variant in (6, 1, 2):
             _lib.check(_lib.lib().cer_set_conv_variant(variant))
             for tma in (0, 1):
                 _lib.check(_lib.lib().cer_set_conv_a_tma(tma))
@@ -192,7 +192,7 @@ def test_conv_a_operand_tma_equals_cpasync(grid):
                 outs[(variant, tma)] = hp(fm, net, inp, P, Kt, 1.0).clone()
     finally:
         _lib.lib().cer_set_conv_a_tma(1)
-        _lib.lib().cer_set_conv_variant(1)
-    for variant in (1, 2):
+        _lib.lib().cer_set_conv_variant(6)
+    for variant in (6, 1, 2):
         assert torch.isfinite(outs[(variant, 0)]).all()
         assert torch.equal(outs[(variant, 0)], outs[(variant, 1)]), variant

@@ -9,7 +9,7 @@ import torch  # noqa: E402
 from cer_mvs_b200 import _lib, synth  # noqa: E402
 from cer_mvs_b200.hotpath import DepthHotPath  # noqa: E402
 
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 _lib.check(_lib.lib().cer_set_conv_variant(variant))
 H, W, V = 1184, 1600, 2
 sc = synth.make_scene(H, W, V, seed=0)
