@@ -41,6 +41,8 @@ SIGNATURES = {
     "cer_resize_bilinear_ac": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cer_disp_to_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cer_multires_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "cer_geo_mats_bytes": (c_size_t, [c_int]),
+    "cer_geometric_filter": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_double, c_double] + [c_void_p] * 10),
     "cer_set_conv_variant": (c_int, [c_int]),
     "cer_set_lookup_variant": (c_int, [c_int]),
     "cer_set_tile_flags": (c_int, [c_int]),

@@ -1,0 +1,66 @@
+"""Geometric-consistency filter of the reference's fusion stage (fusion.py:39-106, 239-249) on one
+fused CUDA kernel (csrc/fusion_ops.cu), under the reference's own function name plus the aggregated form its main loop
+needs.  CUDA tensors only -- no CPU fallback.
+
+    masks, mask, depth_reprojected, x2d_src, y2d_src, rel = check_geometric_consistency(
+        depth_ref, intrinsics_ref, extrinsics_ref, depth_src, intrinsics_src, extrinsics_src, thre1, thre2)
+    geo_mask, depth_est, ratio = geometric_filter(ref_depth, ref_K, ref_E, src_depths, src_Ks, src_Es, thre1, thre2)
+"""
+import torch
+
+from . import _lib
+
+
+def _f32(x, name):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    return x.to(torch.float32).contiguous()
+
+
+def _run(ref_depth, ref_K, ref_E, src_depths, src_Ks, src_Es, thre1, thre2, full):
+    ref_depth, src_depths = _f32(ref_depth, "depth_ref"), _f32(src_depths, "depth_src")
+    ref_K, ref_E = _f32(ref_K, "intrinsics_ref"), _f32(ref_E, "extrinsics_ref")
+    src_Ks, src_Es = _f32(src_Ks, "intrinsics_src"), _f32(src_Es, "extrinsics_src")
+    S, h, w = src_depths.shape
+    if ref_depth.shape != (h, w) or ref_K.shape != (3, 3) or ref_E.shape != (4, 4) or src_Ks.shape != (S, 3, 3) or \
+            src_Es.shape != (S, 4, 4):
+        raise RuntimeError("geometric filter: inconsistent shapes")
+    dev = ref_depth.device
+    L = _lib.lib()
+    ws = torch.empty(L.cer_geo_mats_bytes(S), dtype=torch.uint8, device=dev)
+    geo_mask = torch.empty(h, w, dtype=torch.uint8, device=dev)
+    depth_est = torch.empty(h, w, dtype=torch.float32, device=dev)
+    n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
+    if full:
+        masks = torch.empty(9, S, h, w, dtype=torch.uint8, device=dev)
+        drep, xs, ys, rel = (torch.empty(S, h, w, dtype=torch.float32, device=dev) for _ in range(4))
+        extra = [t.data_ptr() for t in (masks, drep, xs, ys, rel)]
+    else:
+        masks = drep = xs = ys = rel = None
+        extra = [None] * 5
+    with torch.cuda.device(dev):
+        _lib.check(L.cer_geometric_filter(ref_depth.data_ptr(), ref_K.data_ptr(), ref_E.data_ptr(), src_depths.data_ptr(),
+                                          src_Ks.data_ptr(), src_Es.data_ptr(), S, h, w, float(thre1), float(thre2),
+                                          ws.data_ptr(), *extra, geo_mask.data_ptr(), depth_est.data_ptr(),
+                                          n_valid.data_ptr(), _lib.stream_ptr()), "cer_geometric_filter")
+    return masks, drep, xs, ys, rel, geo_mask, depth_est, n_valid
+
+
+def check_geometric_consistency(depth_ref, intrinsics_ref, extrinsics_ref, depth_src, intrinsics_src, extrinsics_src,
+                                thre1=4.4, thre2=1430.):
+    """fusion.py:88-106.  The reference passes the reference view repeated once per source view ([S,h,w], [S,3,3],
+    [S,4,4]); the first copy is used.  Returns (masks: list of 9 bool [S,h,w], mask = masks[-1], depth_reprojected
+    (zero where mask is False), x2d_src, y2d_src, relative_depth_diff)."""
+    masks, drep, xs, ys, rel, _, _, _ = _run(depth_ref[0], intrinsics_ref[0], extrinsics_ref[0], depth_src,
+                                             intrinsics_src, extrinsics_src, thre1, thre2, full=True)
+    mlist = [masks[i].bool() for i in range(9)]
+    return mlist, mlist[-1], drep, xs, ys, rel
+
+
+def geometric_filter(ref_depth, ref_K, ref_E, src_depths, src_Ks, src_Es, thre1, thre2):
+    """One reference view of fusion()'s inner loop (fusion.py:228-251): (geo_mask bool [h,w], depth_est [h,w],
+    geo_mask.float().mean()) without materialising any per-source tensor."""
+    _, _, _, _, _, geo_mask, depth_est, n_valid = _run(ref_depth, ref_K, ref_E, src_depths, src_Ks, src_Es, thre1, thre2,
+                                                       full=False)
+    h, w = geo_mask.shape
+    return geo_mask.bool(), depth_est, float(n_valid.item()) / float(h * w)

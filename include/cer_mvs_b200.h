@@ -186,6 +186,22 @@ int cer_disp_to_depth(const float* disp, float* depth, int h, int w, int flip_ro
 int cer_multires_merge(const float* im1, int h1, int w1, const float* im2, int h2, int w2, float th, float* out,
                        cer_stream_t stream);
 
+/* ---- geometric-consistency filter of fusion.py (csrc/fusion_ops.cu) ----------------------- */
+
+/* reproject_with_depth + check_geometric_consistency (fusion.py:39-106) for one reference view against n_src (<= 10)
+ * source views, and the per-view aggregation of fusion() (fusion.py:239-249), in one kernel.
+ *   depth_ref [h,w], K_ref [3,3], E_ref [4,4] (world -> camera); depth_src [n_src,h,w], K_src [n_src,3,3],
+ *   E_src [n_src,4,4]; thre1 / thre2 as passed to check_geometric_consistency (masks use i/thre1, i/thre2, i = 2..10);
+ *   mats_ws: device scratch of cer_geo_mats_bytes(n_src) bytes.
+ * Per-source outputs (all five or none, may be NULL): masks [9,n_src,h,w] uint8, depth_reprojected [n_src,h,w]
+ * (zero where the i = 10 mask fails), x_src / y_src / rel_diff [n_src,h,w].
+ * Aggregated outputs (each may be NULL): geo_mask [h,w] uint8, depth_est [h,w], n_valid (device int = geo_mask.sum()). */
+size_t cer_geo_mats_bytes(int n_src);
+int cer_geometric_filter(const float* depth_ref, const float* K_ref, const float* E_ref, const float* depth_src,
+                         const float* K_src, const float* E_src, int n_src, int h, int w, double thre1, double thre2,
+                         void* mats_ws, unsigned char* masks, float* depth_reprojected, float* x_src, float* y_src,
+                         float* rel_diff, unsigned char* geo_mask, float* depth_est, int* n_valid, cer_stream_t stream);
+
 /* ConvGRU.forward alone (core/update.py:17-25): net [h*w,64] fp16 NHWC updated in place from
  * inputs inp [h*w,64], dn [h*w,64] (49 disparity-encoder channels + 15 zero), e [h*w,64], all fp16 NHWC. */
 int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e,

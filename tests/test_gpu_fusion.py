@@ -1,0 +1,70 @@
+"""GPU: the fused geometric-consistency filter (csrc/fusion_ops.cu) against golden outputs of the
+reference's own check_geometric_consistency / fusion():239-249 (tests/golden/ops_fusion.npz) and the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+import fusion_oracle as FO
+from cer_mvs_b200 import fusion_ops
+from util import t
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(g, case):
+    depths, K, E = g[f"{case}_depths"], g[f"{case}_K"], g[f"{case}_E"]
+    t1, t2 = (float(v) for v in g[f"{case}_thre"])
+    return depths, K, E, t1, t2
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_check_geometric_consistency_dropin(golden, case):
+    g = golden("ops_fusion")
+    depths, K, E, t1, t2 = _inputs(g, case)
+    S = depths.shape[0] - 1
+    rep = lambda x: t(x).cuda().unsqueeze(0).repeat(S, *([1] * x.ndim))     # noqa: E731  (the reference repeats the ref view)
+    masks, mask, drep, xs, ys, rel = fusion_ops.check_geometric_consistency(
+        rep(depths[0]), rep(K[0]), rep(E[0]), t(depths[1:]).cuda(), t(K[1:]).cuda(), t(E[1:]).cuda(), t1, t2)
+    m = torch.stack(masks).cpu().numpy()
+    assert len(masks) == 9 and torch.equal(mask, masks[-1]) and m.dtype == bool
+    np.testing.assert_allclose(xs.cpu().numpy(), g[f"{case}_x_src"], rtol=0, atol=2e-3)      # pixels
+    np.testing.assert_allclose(ys.cpu().numpy(), g[f"{case}_y_src"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(rel.cpu().numpy(), g[f"{case}_rel"], rtol=0, atol=2e-6)
+    assert (m != g[f"{case}_masks"]).mean() < 2e-3        # thresholds are discontinuous: a few boundary pixels may flip
+    same = (m == g[f"{case}_masks"]).all(axis=(0, 1))
+    np.testing.assert_allclose(drep.cpu().numpy()[:, same], g[f"{case}_depth_reprojected"][:, same], rtol=2e-6)
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_geometric_filter_fused(golden, case):
+    g = golden("ops_fusion")
+    depths, K, E, t1, t2 = _inputs(g, case)
+    keep, depth_est, ratio = fusion_ops.geometric_filter(t(depths[0]).cuda(), t(K[0]).cuda(), t(E[0]).cuda(),
+                                                         t(depths[1:]).cuda(), t(K[1:]).cuda(), t(E[1:]).cuda(), t1, t2)
+    keep, depth_est = keep.cpu().numpy(), depth_est.cpu().numpy()
+    assert (keep != g[f"{case}_geo_mask"]).mean() < 3e-3
+    assert abs(ratio - keep.mean()) < 1e-9 and abs(ratio - g[f"{case}_geo_mask"].mean()) < 3e-3
+    # the averaged depth where every mask bit of the oracle agrees with the reference
+    masks, drep, _, _, _ = FO.check_geometric_consistency(depths[0], K[0], E[0], depths[1:], K[1:], E[1:], t1, t2)
+    same = (masks == g[f"{case}_masks"]).all(axis=(0, 1))
+    close = np.isclose(depth_est, g[f"{case}_depth_est"], rtol=3e-6, atol=0)
+    assert close[same].mean() > 0.998
+
+
+def test_identity_views_known_answer():
+    """Every source view == the reference view: reprojection is exact, every mask passes, depth_est == depth."""
+    h, w, S = 296, 400, 10
+    g = torch.Generator(device="cuda").manual_seed(0)
+    d = torch.rand(h, w, device="cuda", generator=g) * 400 + 400
+    K = torch.tensor([[700.0, 0, w / 2], [0, 700.0, h / 2], [0, 0, 1]], device="cuda")
+    E = torch.eye(4, device="cuda")
+    keep, depth_est, ratio = fusion_ops.geometric_filter(d, K, E, d[None].repeat(S, 1, 1), K[None].repeat(S, 1, 1),
+                                                         E[None].repeat(S, 1, 1), 4.4, 1430.0)
+    assert bool(keep.all()) and ratio == 1.0
+    torch.testing.assert_close(depth_est, d, rtol=2e-6, atol=0)
+
+
+def test_cpu_tensors_raise():
+    with pytest.raises(RuntimeError):
+        fusion_ops.geometric_filter(torch.zeros(4, 4), torch.eye(3), torch.eye(4), torch.zeros(1, 4, 4), torch.eye(3)[None],
+                                    torch.eye(4)[None], 4.4, 1430.0)

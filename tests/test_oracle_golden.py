@@ -1,6 +1,7 @@
 """CPU: the oracle restatement (oracle/cer_oracle.py) against golden outputs of the reference's own
 Python (tests/golden/*.npz, made by oracle/gen_golden.py from /root/reference)."""
 import numpy as np
+import pytest
 import torch
 
 import cer_oracle as O
@@ -111,3 +112,22 @@ def test_io_oracle_matches_reference_functions(golden):
     np.testing.assert_allclose(merged[margin], g["multires_out"][margin], rtol=1e-6)
     picked2 = g["multires_out"] == g["multires_im2"]
     assert 0.2 < picked2.mean() < 0.8                 # both branches of the select are exercised
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_fusion_oracle_matches_reference_functions(golden, case):
+    """oracle/fusion_oracle.py against the reference's check_geometric_consistency + fusion():239-249."""
+    import fusion_oracle as FO
+    g = golden("ops_fusion")
+    depths, K, E, (t1, t2) = g[f"{case}_depths"], g[f"{case}_K"], g[f"{case}_E"], g[f"{case}_thre"]
+    masks, drep, xs, ys, rel = FO.check_geometric_consistency(depths[0], K[0], E[0], depths[1:], K[1:], E[1:], t1, t2)
+    np.testing.assert_allclose(xs, g[f"{case}_x_src"], rtol=0, atol=2e-3)         # pixels, image up to 64 wide
+    np.testing.assert_allclose(ys, g[f"{case}_y_src"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(rel, g[f"{case}_rel"], rtol=0, atol=2e-6)
+    assert (masks != g[f"{case}_masks"]).mean() < 2e-3                            # threshold comparisons are discontinuous
+    same = (masks == g[f"{case}_masks"]).all(axis=(0, 1))
+    np.testing.assert_allclose(drep[:, same], g[f"{case}_depth_reprojected"][:, same], rtol=2e-6)
+    keep, depth_est = FO.aggregate(masks, drep, depths[0])
+    assert (keep != g[f"{case}_geo_mask"]).mean() < 3e-3
+    np.testing.assert_allclose(depth_est[same], g[f"{case}_depth_est"][same], rtol=2e-6)
+    assert 0.3 < g[f"{case}_geo_mask"].mean() < 0.95
