@@ -52,7 +52,9 @@ def test_geometric_filter_fused(golden, case):
 
 
 def test_identity_views_known_answer():
-    """Every source view == the reference view: reprojection is exact, every mask passes, depth_est == depth."""
+    """Every source view == the reference view: every mask passes and depth_est == depth up to the bilinear resampling of a
+    NOISY depth map at coordinates that are only equal to the pixel centres up to fp32 rounding (~1e-5 pixel x neighbour
+    differences of up to 400 -> a few 1e-5 relative)."""
     h, w, S = 296, 400, 10
     g = torch.Generator(device="cuda").manual_seed(0)
     d = torch.rand(h, w, device="cuda", generator=g) * 400 + 400
@@ -61,7 +63,7 @@ def test_identity_views_known_answer():
     keep, depth_est, ratio = fusion_ops.geometric_filter(d, K, E, d[None].repeat(S, 1, 1), K[None].repeat(S, 1, 1),
                                                          E[None].repeat(S, 1, 1), 4.4, 1430.0)
     assert bool(keep.all()) and ratio == 1.0
-    torch.testing.assert_close(depth_est, d, rtol=2e-6, atol=0)
+    torch.testing.assert_close(depth_est, d, rtol=2e-4, atol=0)
 
 
 def test_cpu_tensors_raise():
