@@ -38,26 +38,42 @@ __global__ void __launch_bounds__(kIoThreads) normalize_images_kernel(const floa
 
 // F.interpolate(mode='bilinear', align_corners=True): src index = dst index * (in - 1) / (out - 1), i0 = floor,
 // lambda = frac, second tap clamped to the last pixel; out = wy0 (wx0 a + wx1 b) + wy1 (wx0 c + wx1 d).
+// One thread = VEC consecutive output pixels of one output row (row taps computed once, 16-byte streaming store);
+// blockIdx.x = (plane, output row), so there is no integer division per pixel.
+template <int VEC>
 __global__ void __launch_bounds__(kIoThreads) resize_bilinear_ac_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                                       int planes, int h, int w, int h2, int w2,
-                                                                       float sy, float sx) {
-  const long long total = (long long)planes * h2 * w2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int x2 = (int)(i % w2);
-    const long long r = i / w2;
-    const int y2 = (int)(r % h2);
-    const long long pl = r / h2;
-    const float fy = __fmul_rn(sy, (float)y2), fx = __fmul_rn(sx, (float)x2);
-    const int y0 = min((int)floorf(fy), h - 1), x0 = min((int)floorf(fx), w - 1);
-    const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float* p = src + pl * (long long)h * w;
-    const float a = __ldg(p + (long long)y0 * w + x0), b = __ldg(p + (long long)y0 * w + x1);
-    const float c = __ldg(p + (long long)y1 * w + x0), d = __ldg(p + (long long)y1 * w + x1);
-    const float wy0 = 1.f - ly, wx0 = 1.f - lx;
-    __stcs(dst + i, __fadd_rn(__fmul_rn(wy0, __fadd_rn(__fmul_rn(wx0, a), __fmul_rn(lx, b))),
-                            __fmul_rn(ly, __fadd_rn(__fmul_rn(wx0, c), __fmul_rn(lx, d)))));
+                                                                       int h, int w, int h2, int w2, float sy, float sx) {
+  const int y2 = blockIdx.x % h2;
+  const long long pl = blockIdx.x / h2;
+  const int xq = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+  if (xq >= w2) return;
+  const float fy = __fmul_rn(sy, (float)y2);
+  const int y0 = min((int)floorf(fy), h - 1);
+  const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f);
+  const int y1 = min(y0 + 1, h - 1);
+  const float wy0 = 1.f - ly;
+  const float* r0 = src + (pl * h + y0) * (long long)w;
+  const float* r1 = src + (pl * h + y1) * (long long)w;
+  float o[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const int x2 = min(xq + k, w2 - 1);
+    const float fx = __fmul_rn(sx, (float)x2);
+    const int x0 = min((int)floorf(fx), w - 1);
+    const float lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+    const int x1 = min(x0 + 1, w - 1);
+    const float wx0 = 1.f - lx;
+    const float a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
+    o[k] = __fadd_rn(__fmul_rn(wy0, __fadd_rn(__fmul_rn(wx0, a), __fmul_rn(lx, b))),
+                     __fmul_rn(ly, __fadd_rn(__fmul_rn(wx0, c), __fmul_rn(lx, d))));
+  }
+  float* out = dst + (pl * h2 + y2) * (long long)w2 + xq;
+  if (VEC == 4 && xq + 4 <= w2) {
+    __stcs(reinterpret_cast<float4*>(out), make_float4(o[0], o[1], o[2], o[3]));
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (xq + k < w2) out[k] = o[k];
   }
 }
 
@@ -125,8 +141,14 @@ int cer_resize_bilinear_ac(const float* src, float* dst, int planes, int h, int 
   CER_REQUIRE(src && dst && planes > 0 && h > 0 && w > 0 && h2 > 0 && w2 > 0, "cer_resize_bilinear_ac: bad arguments");
   const float sy = h2 > 1 ? (float)(h - 1) / (float)(h2 - 1) : 0.f;
   const float sx = w2 > 1 ? (float)(w - 1) / (float)(w2 - 1) : 0.f;
-  CER_LAUNCH(KK_LAYOUT, resize_bilinear_ac_kernel, io_grid((long long)planes * h2 * w2), kIoThreads, 0, stream, src, dst,
-             planes, h, w, h2, w2, sy, sx);
+  CER_REQUIRE((long long)planes * h2 <= 0x7fffffffLL, "cer_resize_bilinear_ac: too many output rows");
+  if ((w2 & 3) == 0 && aligned16(dst)) {
+    dim3 grid((unsigned)((long long)planes * h2), ceil_div(w2 / 4, kIoThreads));
+    CER_LAUNCH(KK_LAYOUT, resize_bilinear_ac_kernel<4>, grid, kIoThreads, 0, stream, src, dst, h, w, h2, w2, sy, sx);
+  } else {
+    dim3 grid((unsigned)((long long)planes * h2), ceil_div(w2, kIoThreads));
+    CER_LAUNCH(KK_LAYOUT, resize_bilinear_ac_kernel<1>, grid, kIoThreads, 0, stream, src, dst, h, w, h2, w2, sy, sx);
+  }
   return check_launch("cer_resize_bilinear_ac");
 }
 
