@@ -64,3 +64,50 @@ def geometric_filter(ref_depth, ref_K, ref_E, src_depths, src_Ks, src_Es, thre1,
                                                        full=False)
     h, w = geo_mask.shape
     return geo_mask.bool(), depth_est, float(n_valid.item()) / float(h * w)
+
+
+def fuse_depth_maps(all_depths, all_intrinsics, all_extrinsics, pair_data, glb=0.25, tot_iter=10, images=None):
+    """The view loop of ``fusion()`` (fusion.py:201-299) on the fused filter: bisection of the consistency threshold
+    (``thre`` in log10 units, between -2 and 2) until the mean kept fraction over all reference views meets ``glb``,
+    then the final masks, averaged depths and world-space points.
+
+    all_depths [N,h,w], all_intrinsics [N,3,3], all_extrinsics [N,4,4] (world -> camera), CUDA tensors;
+    pair_data: list of (ref_index, [source indices]); images (optional) [N,h,w,3] in 0..1 for point colours.
+    Returns dict(thre, ratios, masks [N,h,w] bool, depth_est [N,h,w], points: list of [M,3] world xyz per reference
+    view, colors: list of [M,3] uint8 or None)."""
+    all_depths = _f32(all_depths, "all_depths")
+    all_intrinsics, all_extrinsics = _f32(all_intrinsics, "all_intrinsics"), _f32(all_extrinsics, "all_extrinsics")
+    n_images, h, w = all_depths.shape
+    thre_left, thre_right = -2.0, 2.0                                    # fusion.py:201-202
+    masks = torch.zeros(n_images, h, w, dtype=torch.bool, device=all_depths.device)
+    depth_est = torch.zeros(n_images, h, w, device=all_depths.device)
+    thre, ratios = 0.0, []
+    for it in range(tot_iter):
+        thre = (thre_left + thre_right) / 2                              # :206
+        ratios = []
+        for ref_view, src_views in pair_data:
+            src = torch.as_tensor(list(src_views), device=all_depths.device, dtype=torch.long)
+            m, d, r = geometric_filter(all_depths[ref_view], all_intrinsics[ref_view], all_extrinsics[ref_view],
+                                       all_depths[src], all_intrinsics[src], all_extrinsics[src],
+                                       10 ** thre * 4, 10 ** thre * 1300)            # :233-237
+            depth_est[ref_view] = d                                                   # :249
+            masks[ref_view] = m
+            ratios.append(r)                                                          # :253
+        if it < tot_iter - 1:
+            if sum(ratios) / len(ratios) >= glb:                                      # :296-299
+                thre_left = thre
+            else:
+                thre_right = thre
+    points, colors = [], ([] if images is not None else None)
+    ys, xs = torch.meshgrid(torch.arange(h, device=all_depths.device), torch.arange(w, device=all_depths.device),
+                            indexing="ij")
+    for ref_view, _ in pair_data:                                                     # :274-291 (last iteration)
+        valid = masks[ref_view]
+        x, y, dep = xs[valid].double(), ys[valid].double(), depth_est[ref_view][valid].double()
+        xyz_ref = torch.linalg.inv(all_intrinsics[ref_view].double()) @ (torch.stack([x, y, torch.ones_like(x)]) * dep)
+        xyz_world = (torch.linalg.inv(all_extrinsics[ref_view].double()) @
+                     torch.cat([xyz_ref, torch.ones_like(x)[None]]))[:3]
+        points.append(xyz_world.T.float())
+        if images is not None:
+            colors.append((images[ref_view][valid] * 255).to(torch.uint8))
+    return {"thre": thre, "ratios": ratios, "masks": masks, "depth_est": depth_est, "points": points, "colors": colors}

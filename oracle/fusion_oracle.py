@@ -66,3 +66,27 @@ def aggregate(masks, drep, depth_ref):
         keep = keep | (sums[i - 2] >= i)
     depth_est = ((drep.sum(0) + depth_ref) / (sums[8] + 1)).astype(f32)
     return keep, depth_est
+
+
+def fuse(all_depths, all_K, all_E, pair_data, glb=0.25, tot_iter=10):
+    """The view / bisection loop of fusion(), fusion.py:201-299 (without the image and PLY handling)."""
+    n, h, w = all_depths.shape
+    left, right = -2.0, 2.0
+    masks = np.zeros((n, h, w), bool)
+    depth_est = np.zeros((n, h, w), f32)
+    thre, ratios = 0.0, []
+    for it in range(tot_iter):
+        thre = (left + right) / 2
+        ratios = []
+        for ref, srcs in pair_data:
+            srcs = list(srcs)
+            m, drep, _, _, _ = check_geometric_consistency(all_depths[ref], all_K[ref], all_E[ref], all_depths[srcs],
+                                                           all_K[srcs], all_E[srcs], 10 ** thre * 4, 10 ** thre * 1300)
+            masks[ref], depth_est[ref] = aggregate(m, drep, all_depths[ref])
+            ratios.append(float(masks[ref].astype(f32).mean()))
+        if it < tot_iter - 1:
+            if np.mean(ratios) >= glb:
+                left = thre
+            else:
+                right = thre
+    return thre, ratios, masks, depth_est

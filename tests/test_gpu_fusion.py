@@ -70,3 +70,29 @@ def test_cpu_tensors_raise():
     with pytest.raises(RuntimeError):
         fusion_ops.geometric_filter(torch.zeros(4, 4), torch.eye(3), torch.eye(4), torch.zeros(1, 4, 4), torch.eye(3)[None],
                                     torch.eye(4)[None], 4.4, 1430.0)
+
+
+def test_fuse_depth_maps_bisection_loop(golden):
+    """fusion():201-299 -- threshold bisection over all reference views -- against the numpy oracle of the same loop.
+    The bisection is discontinuous (a kept fraction that lands next to ``glb`` can send the two implementations down
+    different branches), so the final threshold is compared up to the last two bisection steps and the masks up to the
+    pixels such a threshold difference moves."""
+    g = golden("ops_fusion")
+    depths, K, E = g["a_depths"], g["a_K"], g["a_E"]
+    n = depths.shape[0]
+    pairs = [(i, [j for j in range(n) if j != i]) for i in range(n)]
+    out = fusion_ops.fuse_depth_maps(t(depths).cuda(), t(K).cuda(), t(E).cuda(), pairs, glb=0.6)
+    thre, ratios, masks, depth_est = FO.fuse(depths, K, E, pairs, glb=0.6)
+    assert abs(out["thre"] - thre) <= 4.0 / 2 ** 8
+    assert abs(np.mean(out["ratios"]) - np.mean(ratios)) < 0.02 and abs(np.mean(ratios) - 0.6) < 0.05
+    m = out["masks"].cpu().numpy()
+    assert (m != masks).mean() < 0.03
+    both = m & masks
+    np.testing.assert_allclose(out["depth_est"].cpu().numpy()[both], depth_est[both], rtol=2e-3)
+    # world points of view 0 (identity pose): x = (u - cx) z / fx
+    p0 = out["points"][0].cpu().numpy()
+    assert p0.shape == (int(m[0].sum()), 3)
+    vs, us = np.nonzero(m[0])
+    z = out["depth_est"].cpu().numpy()[0][m[0]]
+    np.testing.assert_allclose(p0[:, 2], z, rtol=1e-5)
+    np.testing.assert_allclose(p0[:, 0], (us - K[0, 0, 2]) * z / K[0, 0, 0], rtol=1e-4, atol=1e-3)
