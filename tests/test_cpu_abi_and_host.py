@@ -162,3 +162,18 @@ def test_three_fma_division_is_correctly_rounded():
         assert np.array_equal(r32.astype(np.float64), r)          # the residual is exactly representable
         q = (q0.astype(np.float64) + r32.astype(np.float64) * float(rcp)).astype(np.float32)
         assert np.array_equal(q, (xs / d32).astype(np.float32)), d
+
+
+def test_pfm_writer_matches_reference_bytes(tmp_path):
+    """prep.write_pfm / readPFM are host file I/O (no GPU): byte-identical to the file the reference's write_pfm wrote
+    for the same depth map (tests/golden/ops_io.npz), with and without the pre-flipped fast path."""
+    from cer_mvs_b200 import prep
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ops_io.npz")))
+    p = tmp_path / "d.pfm"
+    prep.write_pfm(p, g["depth"])
+    assert open(p, "rb").read() == g["pfm_bytes"].tobytes()
+    prep.write_pfm(p, np.ascontiguousarray(np.flipud(g["depth"])), flipped=True)
+    assert open(p, "rb").read() == g["pfm_bytes"].tobytes()
+    np.testing.assert_array_equal(prep.readPFM(p), g["depth"])
+    with pytest.raises(Exception):
+        prep.write_pfm(p, g["depth"].astype(np.float64))
