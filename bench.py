@@ -10,8 +10,10 @@ features; BASELINE.json configs[1]).  One process per GPU; at N > 1 every rank w
 reference image (replicas, weak scaling, no data-path collective), and the view-sharded single-image
 path (one NCCL all-reduce of the partial cost volume per stage) is timed next to it.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference's algorithm
-(oracle/cer_oracle.py, all host threads) on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own Python (baseline/_ref, imported
+unmodified; its CUDA-only alt_cuda_corr.forward served by the oracle's CPU restatement) on all host threads on a
+bounded sample of the same workload.  The reference's GPU path on the same B200 is timed in the `reference_gpu` block
+of our own line.
 """
 import argparse
 import json
@@ -44,69 +46,55 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (port of the reference algorithm) on a bounded sample
+# CPU baseline / reference arm: the reference's own Python on the host cores (baseline/bench_ref.py)
 # ---------------------------------------------------------------------------------------------
+def host_threads():
+    """All host threads the process may use; set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 def cpu_sample(rows=24, iters=(1, 1)):
-    """Runs rows 0..rows-1 of the 296-row grid (all 400 columns, all 10 views): both volume builds and
-    iters[s] GRU iterations per stage, then extrapolates linearly in pixels and iterations to a full
-    depth map.  Returns (seconds per full depth map, description)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import cer_oracle as O
-    h1, w1 = H // 4, W // 4
-    sc = synth.make_scene(4 * rows, W, V, seed=0)     # same cameras/columns, a band of rows
-    sd = O.to_torch_sd(synth.make_update_weights(seed=0, delta_scale=0.1, delta_bias=0.005))
-    t = torch.from_numpy
-    fm, net, inp = t(sc["fmaps"]), t(sc["net"]), t(sc["inp"])
-    poses, K = t(sc["poses"]).clone(), t(sc["intrinsics"]).clone()
-    K[:, :, :2] /= 4
-    ii, jj = [0] * V, list(range(1, V + 1))
-    disp = torch.zeros(1, 1, rows, w1)
-    t_build = t_iter = 0.0
-    n_it = 0
-    with torch.no_grad():
-        for stage, (D, incre, _) in enumerate(O.stage_params(CASCADE)):
-            t0 = time.perf_counter()
-            pyr, origin = O.build_volume(fm, poses, K, ii, jj, D, incre, disp, stage == 0)
-            t_build += time.perf_counter() - t0
-            for _ in range(iters[stage]):
-                t0 = time.perf_counter()
-                cf = O.lookup(pyr, origin, D, incre, disp[:, ii])
-                net, delta = O.update_block(sd, net, inp, disp, cf, stage, autocast=False)
-                disp = disp + delta
-                t_iter += time.perf_counter() - t0
-                n_it += 1
-    scale_px = h1 / rows
-    total_iters = sum(c[2] for c in CASCADE)
-    full = t_build * scale_px + (t_iter / n_it) * total_iters * scale_px
-    desc = (f"rows 0..{rows - 1} of {h1} x {w1} cols x {V} views: both volume builds + {iters[0]}+{iters[1]} of "
-            f"16+16 iterations, fp32, extrapolated linearly in pixels and iterations ({t_build + t_iter:.1f}s of CPU work)")
-    return full, desc
+    """One bounded sample of the reference on the host: (seconds per full depth map, description, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import bench_ref
+    full, desc, _ = bench_ref.reference_cpu(H, W, V, CASCADE, rows, iters)
+    return full, desc, "reference"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = host_threads()
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import bench_ref
     for _ in range(args.warmup):
-        cpu_sample(rows=8, iters=(1, 1))
+        cpu_sample(rows=args.ref_rows, iters=(1, 1))
     times = []
-    desc = ""
+    desc = kind = ""
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        full, desc = cpu_sample(rows=args.ref_rows, iters=(1, 1))
+        full, desc, kind = cpu_sample(rows=args.ref_rows, iters=(1, 1))
         times.append(full)
     wall = time.perf_counter() - t0
     sec = float(np.mean(times))
     val = 1.0 / sec
+    cfg1_s = bench_ref.reference_cpu_cfg1()          # one whole, un-extrapolated depth map of BASELINE configs[0]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "depth-maps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU port of the reference algorithm (oracle/cer_oracle.py); the "
-                   "reference's own Python cannot travel to the GPU box and its alt_cuda_corr is CUDA-only"},
-        "cpu_baseline": {"value": val, "unit": "depth-maps/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": {"workload": WORKLOAD, "parallelism": "host cores", "l2": "n/a (CPU)",
+                   "engine": "reference Python (baseline/_ref), hot path only"},
+        "cpu_baseline": {"value": val, "unit": "depth-maps/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "depth-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cfg1_whole_depth_map": {"seconds": cfg1_s, "depth_maps_per_s": 1.0 / cfg1_s, "extrapolated": False,
+                                 "workload": "BASELINE configs[0]: 448x576, 2 source views, 2+2 iterations, fp32"},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -378,10 +366,34 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # one bounded sample of ~15-20 s of CPU work: a third of the image rows, 2+2 iterations
-        full, desc = cpu_sample(rows=4 * args.ref_rows, iters=(2, 2))
-        cpu = {"value": 1.0 / full, "unit": "depth-maps/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": desc}
+        # one bounded sample of ~10-20 s of CPU work: 24 of 296 rows, 1+1 iterations
+        cores = host_threads()
+        full, desc, kind = cpu_sample(rows=3 * args.ref_rows, iters=(1, 1))
+        cpu = {"value": 1.0 / full, "unit": "depth-maps/s", "cores": cores, "kind": kind, "sample": desc}
+
+    # ---- the reference's GPU path on this same B200: its Python, its kernel, real autocast ----
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        try:
+            import bench_ref
+            import refrun
+            if refrun.available("gpu"):
+                r = bench_ref.reference_gpu(H, W, V, sc, sd, {"16+16": CASCADE, "8+8": [(64, 64, 8), (-1, 320, 8)]}, dev)
+                ref_gpu = {
+                    "what": "UNMODIFIED reference on this GPU: core/raft.py:75-108 with its own CorrBlock / UpdateBlock, "
+                            "its own alt_cuda_corr kernel (sm_100 build), torch.cuda.amp.autocast; stub encoders; "
+                            "inputs resident; CUDA events",
+                    "ms_per_depth_map_16_16": r["16+16"], "depth_maps_per_s_16_16": 1e3 / r["16+16"],
+                    "ms_per_depth_map_8_8": r["8+8"], "depth_maps_per_s_8_8": 1e3 / r["8+8"],
+                    "speedup_16_16": (ms / args.steps) and r["16+16"] / (ms / args.steps),
+                    "speedup_8_8": r["8+8"] / ms8, "north_star_target": ">= 4x",
+                    "corr_kernels": bench_ref.corr_kernel_legs(H, W, V, sc, dev),
+                }
+            else:
+                ref_gpu = {"unavailable": "baseline/_ref or oracle/_ref did not travel"}
+        except Exception as e:  # noqa: BLE001   the checker must never break the product's line
+            ref_gpu = {"unavailable": repr(e)[:300]}
 
     if rank == 0:
         line = {
@@ -398,7 +410,7 @@ def run_ours(args):
             "gpu_launches": launches, "iters_8_8": {"value": world * 1e3 / ms8, "unit": "depth-maps/s", "ms_per_step": ms8,
                                                   "note": "same workload with the reference's default 8+8 iterations"},
             "clocks": clk, "roofline": roof, "lookup_roofline": lookup_roof,
-            "cpu_baseline": cpu, "kernels": kernels,
+            "cpu_baseline": cpu, "reference_gpu": ref_gpu, "kernels": kernels,
         }
         if viewshard:
             line["viewshard"] = viewshard
@@ -413,8 +425,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-rows", type=int, default=24, help="rows of the 296-row grid in one CPU sample")
+    ap.add_argument("--ref-rows", type=int, default=8, help="rows of the 296-row grid in one CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-this-GPU leg")
     ap.add_argument("--profile-step", action="store_true", help="ncu helper: warm-up + one eager step only")
     ap.add_argument("--conv-variant", type=int, default=None, help="cer_set_conv_variant (A/B experiments)")
     args = ap.parse_args()

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/cer_mvs_b200.h"
 
 namespace cer {
@@ -30,6 +32,15 @@ int check_launch(const char* what);
       return (int)e_;                                                               \
     }                                                                               \
   } while (0)
+
+// One-time-per-DEVICE guard for cudaFuncSetAttribute (the attribute lives in the device's context, so a process-wide
+// flag would leave the kernels of a second GPU unconfigured): true exactly once per (guard, current device).
+static inline bool first_time_on_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return !(mask.fetch_or(bit) & bit);
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

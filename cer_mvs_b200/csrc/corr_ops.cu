@@ -467,12 +467,11 @@ int cer_lookup_strided(const float* volume, int slots, const float* origin, cons
   CER_REQUIRE(D <= 1024, "cer_lookup: D > 1024 unsupported");
   const long long px = (long long)h * w;
   if (lookup_variant() >= 2 && radius == 5 && num_levels == 3 && (D == 64 || D == 44) && px < (1ll << 31) - 64) {
-    static bool configured = false;
+    static std::atomic<unsigned long long> configured{0};
     const size_t smem2 = (size_t)kLookupV2Warps * kPyrWarpFloats * sizeof(float);
-    if (!configured) {
+    if (first_time_on_device(configured)) {
       CER_CUDA(cudaFuncSetAttribute(lookup_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       CER_CUDA(cudaFuncSetAttribute(lookup_v2_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      configured = true;
     }
     dim3 grid2(ceil_div(px, kLookupV2Warps * 32), slots);
     if (D == 64)

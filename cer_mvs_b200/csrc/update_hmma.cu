@@ -832,8 +832,8 @@ void set_lookup_variant(int v) { g_lookup_variant = v; }
 
 // Opt in to >48 KB dynamic shared memory once per process (not capturable, so done up front).
 int update_configure() {
-  static bool done = false;
-  if (done) return CER_OK;
+  static std::atomic<unsigned long long> done{0};
+  if (!first_time_on_device(done)) return CER_OK;
   int rc;
   if ((rc = tc_configure())) return rc;
   if ((rc = configure_conv<64, EPI_RELU>())) return rc;
@@ -850,7 +850,6 @@ int update_configure() {
                                 (int)lookup_enc1_v3_smem()));
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)lookup_enc1_v3_smem()));
-  done = true;
   return CER_OK;
 }
 

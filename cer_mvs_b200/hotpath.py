@@ -43,6 +43,10 @@ class DepthHotPath:
         self.h1, self.w1, self.max_views = int(h1), int(w1), int(max_views)
         self.stages = stage_params(cascade)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DepthHotPath: a CUDA device is required (cer_mvs_b200 has no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         cfg = _lib.PlanConfig()
         cfg.h, cfg.w, cfg.max_views, cfg.n_stages = self.h1, self.w1, self.max_views, len(self.stages)
         for s, (D, incre, iters) in enumerate(self.stages):
@@ -84,23 +88,62 @@ class DepthHotPath:
         K[:, :2] /= 4
         return P.contiguous(), K.contiguous()
 
-    def _check_maps(self, fmaps, net, inp):
+    def _check_maps(self, fmaps, net, inp, poses=None, intrinsics=None, out=None):
+        """Shapes, dtypes, devices of everything whose raw pointer goes to the C ABI (device entry points)."""
         if fmaps.dim() != 5 or fmaps.shape[0] != 1 or fmaps.shape[2] != 64 or tuple(fmaps.shape[3:]) != (self.h1, self.w1):
             raise RuntimeError(f"fmaps must be [1,V+1,64,{self.h1},{self.w1}]")
         n_views = fmaps.shape[1] - 1
         if not 1 <= n_views <= self.max_views:
             raise RuntimeError(f"number of source views {n_views} outside 1..{self.max_views}")
-        for t in (fmaps, net, inp):
+        for name, t in (("fmaps", fmaps), ("net", net), ("inp", inp)):
             if not t.is_cuda:
                 raise RuntimeError("DepthHotPath: device tensors expected (use run_host for host buffers)")
+            if t.device != self.device:
+                raise RuntimeError(f"DepthHotPath: {name} lives on {t.device}, the plan on {self.device}")
             if t.dtype not in (torch.float16, torch.float32):
                 raise RuntimeError("DepthHotPath: float16 or float32 maps expected")
+        for name, t in (("net", net), ("inp", inp)):
+            if t.numel() != 64 * self.h1 * self.w1 or tuple(t.shape[-3:]) != (64, self.h1, self.w1):
+                raise RuntimeError(f"{name} must be [1,1,64,{self.h1},{self.w1}]")
         if net.dtype != inp.dtype:
             raise RuntimeError("net and inp must share a dtype")
+        self._check_cameras(poses, intrinsics, n_views)
+        if out is not None:
+            if not (out.is_cuda and out.device == self.device and out.dtype == torch.float32 and out.is_contiguous()
+                    and out.numel() == self.h1 * self.w1):
+                raise RuntimeError(f"out must be a contiguous float32 tensor of {self.h1}x{self.w1} elements on {self.device}")
+        return n_views
+
+    @staticmethod
+    def _check_cameras(poses, intrinsics, n_views):
+        if poses is not None and int(np.prod(tuple(poses.shape))) != (n_views + 1) * 16:
+            raise RuntimeError(f"poses must hold {n_views + 1} 4x4 matrices (reference + source views)")
+        if intrinsics is not None and int(np.prod(tuple(intrinsics.shape))) != (n_views + 1) * 9:
+            raise RuntimeError(f"intrinsics must hold {n_views + 1} 3x3 matrices (reference + source views)")
+
+    def _check_host(self, fm, nt, ip, poses, intrinsics, o, who):
+        """The C side copies (n_views+1)*64*px elements from `fm`, 64*px from `nt` / `ip` and writes px floats into `o`:
+        every size is checked here, a mismatch would be an out-of-bounds host access."""
+        if fm.ndim != 5 or fm.shape[0] != 1 or fm.shape[2] != 64 or tuple(fm.shape[3:]) != (self.h1, self.w1):
+            raise RuntimeError(f"{who}: fmaps must be [1,V+1,64,{self.h1},{self.w1}]")
+        n_views = fm.shape[1] - 1
+        if not 1 <= n_views <= self.max_views:
+            raise RuntimeError(f"{who}: number of source views {n_views} outside 1..{self.max_views}")
+        for name, a in (("fmaps", fm), ("net", nt), ("inp", ip)):
+            if a.dtype not in (np.float16, np.float32) or not a.flags["C_CONTIGUOUS"]:
+                raise RuntimeError(f"{who}: {name}: contiguous float16/float32 array expected")
+        for name, a in (("net", nt), ("inp", ip)):
+            if a.size != 64 * self.h1 * self.w1 or tuple(a.shape[-3:]) != (64, self.h1, self.w1):
+                raise RuntimeError(f"{who}: {name} must be [1,1,64,{self.h1},{self.w1}]")
+        if nt.dtype != ip.dtype:
+            raise RuntimeError(f"{who}: net and inp must share a dtype")
+        self._check_cameras(poses, intrinsics, n_views)
+        if o.dtype != np.float32 or not o.flags["C_CONTIGUOUS"] or o.size != self.h1 * self.w1 or not o.flags["WRITEABLE"]:
+            raise RuntimeError(f"{who}: out must be a writable contiguous float32 array of {self.h1}x{self.w1} elements")
         return n_views
 
     def __call__(self, fmaps, net, inp, poses, intrinsics, scale=1.0, out=None):
-        n_views = self._check_maps(fmaps, net, inp)
+        n_views = self._check_maps(fmaps, net, inp, poses, intrinsics, out)
         with torch.cuda.device(self.device):
             P, K = self._prep_cameras(poses, intrinsics, scale)
             fmaps, net, inp = fmaps.contiguous(), net.contiguous(), inp.contiguous()
@@ -117,18 +160,15 @@ class DepthHotPath:
         def as_np(x):
             return x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
         fm, nt, ip = as_np(fmaps), as_np(net), as_np(inp)
-        n_views = fm.shape[1] - 1
+        if out is None:
+            out = np.empty((1, 1, self.h1, self.w1), np.float32)
+        o = as_np(out)
+        n_views = self._check_host(fm, nt, ip, as_np(poses), as_np(intrinsics), o, "run_host")
         P = np.array(as_np(poses), dtype=np.float32).reshape(-1, 4, 4)
         if scale is not None:
             P[:, :3, 3] *= np.float32(scale)
         K = np.array(as_np(intrinsics), dtype=np.float32).reshape(-1, 3, 3)
         K[:, :2] /= 4
-        if out is None:
-            out = np.empty((1, 1, self.h1, self.w1), np.float32)
-        o = as_np(out)
-        for a in (fm, nt, ip):
-            if a.dtype not in (np.float16, np.float32) or not a.flags["C_CONTIGUOUS"]:
-                raise RuntimeError("run_host: contiguous float16/float32 arrays expected")
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().cer_plan_run_host(
                 self._plan, fm.ctypes.data, int(fm.dtype == np.float16), nt.ctypes.data, ip.ctypes.data,
@@ -142,18 +182,15 @@ class DepthHotPath:
         def as_np(x):
             return x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
         fm, nt, ip = as_np(fmaps), as_np(net), as_np(inp)
-        n_views = fm.shape[1] - 1
+        if out is None:
+            out = torch.empty(1, 1, self.h1, self.w1).pin_memory()
+        o = as_np(out)
+        n_views = self._check_host(fm, nt, ip, as_np(poses), as_np(intrinsics), o, "submit_host")
         P = np.array(as_np(poses), dtype=np.float32).reshape(-1, 4, 4)
         if scale is not None:
             P[:, :3, 3] *= np.float32(scale)
         K = np.array(as_np(intrinsics), dtype=np.float32).reshape(-1, 3, 3)
         K[:, :2] /= 4
-        if out is None:
-            out = torch.empty(1, 1, self.h1, self.w1).pin_memory()
-        o = as_np(out)
-        for a in (fm, nt, ip):
-            if a.dtype not in (np.float16, np.float32) or not a.flags["C_CONTIGUOUS"]:
-                raise RuntimeError("submit_host: contiguous float16/float32 arrays expected")
         self._keep = getattr(self, "_keep", [])[-3:] + [(fm, nt, ip, P, K, o)]     # keep host buffers alive while in flight
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().cer_plan_submit_host(
@@ -173,7 +210,7 @@ class DepthHotPath:
         band is the default; banding is for slower links / more ranks."""
         import torch.distributed as dist
         from .dist import view_range
-        n_views = self._check_maps(fmaps, net, inp)
+        n_views = self._check_maps(fmaps, net, inp, poses, intrinsics, out)
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         vb, ve = view_range(n_views, rank, world)
         L = _lib.lib()

@@ -86,6 +86,24 @@ def test_e2e_fp32(golden):
         assert err < 1e-4, (name, err)
 
 
+def test_e2e_cfg1_full_size(golden):
+    """BASELINE configs[0] at its full size (448x576, 2 views, 2+2 iterations, fp32): the oracle against the
+    reference's own un-extrapolated CPU run (oracle/gen_golden_cfg1.py)."""
+    g = golden("e2e_fp32_cfg1")
+    Hc, Wc, Vc = synth.CONFIGS["cfg1_dtu_448x576_v2"]
+    seed = int(g["seed"])
+    sc = synth.make_scene(Hc, Wc, Vc, seed=seed)
+    sd = O.to_torch_sd(synth.make_update_weights(seed=seed, delta_scale=float(g["delta_scale"]),
+                                                 delta_bias=float(g["delta_bias"])))
+    pre = t(synth.make_context_pre(Hc // 4, Wc // 4, seed=seed))
+    cascade = [tuple(int(v) for v in row) for row in g["cascade"]]
+    out = O.hot_path(sd, t(sc["fmaps"]), torch.tanh(pre[:, :, :64]), torch.relu(pre[:, :, 64:]), t(sc["poses"]),
+                     t(sc["intrinsics"]), cascade=cascade, scale=1.0, autocast=False).numpy()
+    assert out.shape == g["disp"].shape == (1, 1, 112, 144)
+    err = rel_l1(out, g["disp"])
+    assert err < 1e-4, err
+
+
 def test_e2e_autocast_emulation(golden):
     """The fp16-rounding emulation against the reference run under torch.autocast('cpu', float16)
     (proxy for the GPU autocast path, core/raft.py:55)."""
