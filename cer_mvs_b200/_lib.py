@@ -31,7 +31,6 @@ SIGNATURES = {
                                       c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p]),
     "cer_set_build_variant": (c_int, [c_int]),
-    "cer_set_build_reuse": (c_int, [c_int]),
     "cer_pool_pairs": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "cer_lookup": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_int,
                            c_int, c_void_p]),

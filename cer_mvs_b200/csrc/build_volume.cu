@@ -228,15 +228,6 @@ struct Slice16 {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
   }
-  // load only if `need` (a predicated-off lane sends nothing to L1); the registers keep zeros otherwise
-  __device__ __forceinline__ void load_if(const void* p, bool need) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0u;
-    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %9, 0;\n"
-                 " @q ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n}"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
-                 : "l"(p), "r"((uint32_t)need));
-  }
   __device__ __forceinline__ float dot(const Slice16& o) const {
     float d = fhfma_lo(v[0], o.v[0], 0.f);
     d = fhfma_hi(v[0], o.v[0], d);
@@ -251,15 +242,11 @@ struct Slice16 {
 
 constexpr int kH16Chunks = 4;   // chunks of 4 hypotheses per block in sequence
 
-// REUSE: consecutive hypotheses of a pixel that land in the same or a neighbouring source cell (the second cascade stage
-// steps ~0.7 source pixels per hypothesis) share corner rows, and the dot of the reference pixel with a corner row does
-// not depend on the hypothesis: the four dots of the previous sample are kept and a corner whose row was already seen
-// is not fetched again (its load is predicated off, so it costs no L1 wavefront -- the limiter of this kernel).  Same
-// operands in the same order, so the result is bit-identical.
-// ALL: every lane projects all four samples of its pixel itself (4x redundant arithmetic, no shared-memory slots, no
-// warp barriers): trades ~35 % more instructions for ~23 % fewer L1 wavefronts (cer_set_build_variant(3)).
-template <bool REUSE, bool ALL>
-__global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
+// The L1-gather formulation (cer_set_build_variant(1) / CER_BUILD=gather; the A/B partner of the shared-memory-staged
+// tcgen05 build in build_volume_tc.cu and the path used for row bands of odd geometry): a 4-lane group owns a pixel, the
+// owner lane projects hypothesis d0 + lane and publishes clamped corner offsets + weights through shared memory, every
+// lane fetches 16 channels of a corner row with one 256-bit load.
+__global__ void __launch_bounds__(256, 4) build_volume_h16_kernel(
     const __half* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
     const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
     float lo_origin, float* __restrict__ origin_out, float* __restrict__ volume, float out_scale, int per_view,
@@ -267,8 +254,7 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
   __shared__ float sP[kMaxPairs][12];
   __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
   // per 4-lane group: 4 samples x {4 byte offsets, 4 weights} = 32 words, padded to 36: a quarter-warp (two groups)
-  // then reads / writes its two 16-byte slots in different banks (ncu: every LDS.128 / STS.128 of the unpadded layout
-  // took 8 wavefronts instead of 4, a third of this L1-bound kernel's wavefronts)
+  // then reads / writes its two 16-byte slots in different banks
   constexpr int kGrpWords = 36;
   __shared__ __align__(16) int sS[64 * kGrpWords];
   for (int t = threadIdx.x; t < n_pairs * 12; t += blockDim.x) sP[t / 12][t % 12] = Pij[(t / 12) * 16 + (t % 12)];
@@ -280,12 +266,9 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
 
   const int lane = threadIdx.x & 3;
   const long long px = (long long)h * w;
-  // a block = an 8 x 8 pixel tile (a warp = one tile row): neighbouring pixels sample neighbouring source pixels at the
-  // same hypothesis, so a 2-D tile re-uses corner rows in both directions out of L1 (the kernel is bound by L1 misses)
+  // a block = an 8 x 8 pixel tile (a warp = one tile row); grid = (hypothesis-chunk groups, pixel tiles)
   const int tiles_x = (w + 7) >> 3;
   const int pl = threadIdx.x >> 2;
-  // grid = (hypothesis-chunk groups, pixel tiles): the blocks of one pixel tile are scheduled together, so the tile's
-  // source neighbourhoods are pulled into L2 once per stage instead of once per hypothesis range
   const int x_ = (blockIdx.y % tiles_x) * 8 + (pl & 7), y_ = y_begin + (blockIdx.y / tiles_x) * 8 + (pl >> 3);
   const bool valid = x_ < w && y_ < h;
   const int x = valid ? x_ : w - 1, y = valid ? y_ : h - 1;
@@ -306,9 +289,6 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
     if (d0 >= D) break;
     const int d = d0 + lane;
     const float dval = __fadd_rn(__fmul_rn((float)(min(d, D - 1) - D / 2), incre), org);   // corr.py:56,66
-    float dvals[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) dvals[s] = __fadd_rn(__fmul_rn((float)(min(d0 + s, D - 1) - D / 2), incre), org);
     float acc = 0.f;
     for (int k = 0; k < n_pairs; ++k) {
       const int ri = sI[k];
@@ -320,10 +300,10 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
       const float* P = sP[k];
       // X = Pij . (x, y, 1, d), /X2, clamp (corr.py:88), floor; clamped corner offsets (every load legal) and row / column
       // weights with out-of-range rows / columns zeroed (NaN coordinates keep NaN weights like the reference)
-      const float bx = fmaf(P[1], yf, P[0] * xf) + P[2], by = fmaf(P[5], yf, P[4] * xf) + P[6];
-      const float bz = fmaf(P[9], yf, P[8] * xf) + P[10];
-      auto project = [&](float dv, int4& o4, float4& wt) {
-        const float X0 = fmaf(P[3], dv, bx), X1 = fmaf(P[7], dv, by), X2 = fmaf(P[11], dv, bz);
+      {
+        const float bx = fmaf(P[1], yf, P[0] * xf) + P[2], by = fmaf(P[5], yf, P[4] * xf) + P[6];
+        const float bz = fmaf(P[9], yf, P[8] * xf) + P[10];
+        const float X0 = fmaf(P[3], dval, bx), X1 = fmaf(P[7], dval, by), X2 = fmaf(P[11], dval, bz);
         float u = __fdiv_rn(X0, X2), v = __fdiv_rn(X1, X2);
         u = u < -1e4f ? -1e4f : (u > 1e4f ? 1e4f : u);
         v = v < -1e4f ? -1e4f : (v > 1e4f ? 1e4f : v);
@@ -332,69 +312,33 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
         const int ix = (int)fu, iy = (int)fv;
         const int y0c = min(max(iy, 0), h - 1), y1c = min(max(iy + 1, 0), h - 1);
         const int x0c = min(max(ix, 0), w - 1), x1c = min(max(ix + 1, 0), w - 1);
+        float4 wt;
         wt.x = (iy >= 0 && iy < h) ? 1.f - dy : ((dy != dy) ? dy : 0.f);
         wt.y = (iy + 1 >= 0 && iy + 1 < h) ? dy : ((dy != dy) ? dy : 0.f);
         wt.z = (ix >= 0 && ix < w) ? 1.f - dx : ((dx != dx) ? dx : 0.f);
         wt.w = (ix + 1 >= 0 && ix + 1 < w) ? dx : ((dx != dx) ? dx : 0.f);
-        o4 = make_int4((y0c * w + x0c) * 128, (y0c * w + x1c) * 128, (y1c * w + x0c) * 128, (y1c * w + x1c) * 128);
-      };
-      if (!ALL) {      // the owner lane resolves sample d0 + lane once and publishes it through shared memory
-        int4 o4;
-        float4 wt;
-        project(dval, o4, wt);
         int4* slot = reinterpret_cast<int4*>(grp + lane * 8);
-        slot[0] = o4;
+        slot[0] = make_int4((y0c * w + x0c) * 128, (y0c * w + x1c) * 128, (y1c * w + x0c) * 128, (y1c * w + x1c) * 128);
         reinterpret_cast<float4*>(slot)[1] = wt;
         __syncwarp();
       }
       float part[4];
-      int4 po = make_int4(-1, -1, -1, -1);          // corner rows (byte offsets) and dots of the previous sample
-      float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        int4 o4;
-        float4 wt;
-        if (ALL) {
-          project(dvals[s], o4, wt);
-        } else {
-          o4 = *reinterpret_cast<const int4*>(grp + s * 8);
-          wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
-        }
-        float d00, d01, d10, d11;
-        if (REUSE) {
-          // which corners were seen by the previous sample (uniform over the 4 lanes of a pixel)
-          auto seen = [&](int off, float& d) {
-            const bool hx = off == po.x, hy = off == po.y, hz = off == po.z, hw = off == po.w;
-            d = hx ? pd.x : hy ? pd.y : hz ? pd.z : pd.w;
-            return hx || hy || hz || hw;
-          };
-          float c00, c01, c10, c11;
-          const bool h00 = seen(o4.x, c00), h01 = seen(o4.y, c01), h10 = seen(o4.z, c10), h11 = seen(o4.w, c11);
-          Slice16 a, b, c, e;                        // all needed loads in flight together
-          a.load_if(ptr_add_u32(img2, (uint32_t)o4.x), !h00);
-          b.load_if(ptr_add_u32(img2, (uint32_t)o4.y), !h01);
-          c.load_if(ptr_add_u32(img2, (uint32_t)o4.z), !h10);
-          e.load_if(ptr_add_u32(img2, (uint32_t)o4.w), !h11);
-          d00 = h00 ? c00 : f1.dot(a);
-          d01 = h01 ? c01 : f1.dot(b);
-          d10 = h10 ? c10 : f1.dot(c);
-          d11 = h11 ? c11 : f1.dot(e);
-          po = o4;
-          pd = make_float4(d00, d01, d10, d11);
-        } else {
-          Slice16 f2;
-          f2.load(ptr_add_u32(img2, (uint32_t)o4.x));
-          d00 = f1.dot(f2);
-          f2.load(ptr_add_u32(img2, (uint32_t)o4.y));
-          d01 = f1.dot(f2);
-          f2.load(ptr_add_u32(img2, (uint32_t)o4.z));
-          d10 = f1.dot(f2);
-          f2.load(ptr_add_u32(img2, (uint32_t)o4.w));
-          d11 = f1.dot(f2);
-        }
+        const int4 o4 = *reinterpret_cast<const int4*>(grp + s * 8);
+        const float4 wt = *reinterpret_cast<const float4*>(grp + s * 8 + 4);
+        Slice16 f2;
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.x));
+        const float d00 = f1.dot(f2);
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.y));
+        const float d01 = f1.dot(f2);
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.z));
+        const float d10 = f1.dot(f2);
+        f2.load(ptr_add_u32(img2, (uint32_t)o4.w));
+        const float d11 = f1.dot(f2);
         part[s] = ((d00 * wt.x) * wt.z + (d01 * wt.x) * wt.w) + ((d10 * wt.y) * wt.z + (d11 * wt.y) * wt.w);
       }
-      if (!ALL) __syncwarp();      // the slots are rewritten for the next view
+      __syncwarp();      // the slots are rewritten for the next view
       // butterfly over the 4 lanes: lane L ends with the total of sample L
       float k2[2];
 #pragma unroll
@@ -421,24 +365,15 @@ __global__ void __launch_bounds__(256, REUSE ? 3 : 4) build_volume_h16_kernel(
 namespace cer {
 int build_volume_tc(const void* feats, const float* Pij, const int* ii, const int* jj, int n_pairs,
                     const float* disp_in, int shift, int D, float incre, float lo_origin, float* origin,
-                    float* volume, float out_scale, int per_view, int h, int w, cudaStream_t stream);
-// corner-dot reuse in the FHFMA build kernel: 0 = never (default), 1 = always, -1 = refinement stages only
-// (CER_BUILD_REUSE).  Measured on B200 (cfg 2): it removes ~45 % of the stage-1 corner fetches but needs 80 registers
-// (3 CTAs per SM instead of 4) and 36 more instructions per sample: 1.83 ms / stage against 1.75 ms without it --
-// the kernel is bound by the latency of its L1 misses at the occupancy it has, not by L1 wavefronts alone.
-static int g_build_reuse = -2;
-static int build_reuse() {
-  if (g_build_reuse == -2) {
-    const char* e = getenv("CER_BUILD_REUSE");
-    g_build_reuse = e ? atoi(e) : 0;
-  }
-  return g_build_reuse;
-}
+                    float* volume, float out_scale, int per_view, int h, int w, int y_begin, int y_end,
+                    cudaStream_t stream);
+// 0 = shared-memory-staged source boxes + tcgen05 (build_volume_tc.cu, default for fp16 features);
+// 1 = L1 row gather with FHFMA (this file).  fp32 features always take the generic gather kernel.
 static int g_build_variant = -1;
 static int build_variant() {
   if (g_build_variant < 0) {
     const char* e = getenv("CER_BUILD");
-    g_build_variant = (e && !strcmp(e, "tc")) ? 1 : (e && !strcmp(e, "l8")) ? 2 : (e && !strcmp(e, "noslots")) ? 3 : 0;
+    g_build_variant = (e && !strcmp(e, "gather")) ? 1 : 0;
   }
   return g_build_variant;
 }
@@ -447,16 +382,9 @@ static int build_variant() {
 using namespace cer;
 
 extern "C" int cer_set_build_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 3,
-              "cer_set_build_variant: 0 FHFMA gather, 4 lanes x 256-bit loads (default); 1 tcgen05 gather; 2 FHFMA gather, "
-              "8 lanes; 3 FHFMA gather, 4 lanes, every lane projects its pixel's samples itself (no shared-memory slots)");
+  CER_REQUIRE(variant >= 0 && variant <= 1,
+              "cer_set_build_variant: 0 TMA-staged source boxes + tcgen05 (default); 1 L1 row gather (FHFMA)");
   g_build_variant = variant;
-  return CER_OK;
-}
-
-extern "C" int cer_set_build_reuse(int mode) {
-  CER_REQUIRE(mode >= -1 && mode <= 1, "cer_set_build_reuse: -1 automatic (refinement stages), 0 never, 1 always");
-  g_build_reuse = mode;
   return CER_OK;
 }
 
@@ -486,35 +414,21 @@ extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const flo
   CER_REQUIRE(n_pairs > 0 && n_pairs <= kMaxPairs, "cer_build_volume: n_pairs must be 1..%d", kMaxPairs);
   CER_REQUIRE(D > 0 && h > 0 && w > 0, "cer_build_volume: bad sizes");
   CER_REQUIRE(aligned16(feats), "cer_build_volume: feats must be 16-byte aligned");
-  // fp16 features: dot products on tcgen05 (build_volume_tc.cu); a 128-entry tile must span <= 4 pixels
-  CER_REQUIRE(whole || (feats_f16 && (build_variant() == 0 || build_variant() == 3)),
-              "cer_build_volume_rows: row bands are implemented by the FHFMA 4-lane kernel (fp16 features) only");
-  if (feats_f16 && D >= 43 && D <= 4096 && build_variant() == 1)
+  CER_REQUIRE(whole || feats_f16, "cer_build_volume_rows: row bands need fp16 features");
+  if (feats_f16 && build_variant() == 0 && (reinterpret_cast<uintptr_t>(feats) & 127) == 0)
     return build_volume_tc(feats, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale,
-                           per_view, h, w, (cudaStream_t)stream);
+                           per_view, h, w, y_begin, y_end, (cudaStream_t)stream);
   const long long px = (long long)h * w;
-  const int chunks = ceil_div(D, 8);
-  dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
-  if (feats_f16 && build_variant() != 2) {
+  if (feats_f16) {
     dim3 g16(ceil_div(ceil_div(D, 4), kH16Chunks), ((w + 7) / 8) * ((y_end - y_begin + 7) / 8));
     CER_REQUIRE(g16.y <= 65535u, "cer_build_volume: image too large for the tile grid (%u tiles)", g16.y);
-    // corner-dot reuse (opt-in experiment, see build_reuse()): neighbouring hypotheses of the refinement stages fall
-    // into neighbouring source cells; the first stage steps several source pixels per hypothesis
-    const bool reuse = build_reuse() == 1 || (build_reuse() < 0 && !shift);
-    if (reuse)
-      CER_LAUNCH(KK_BUILD, (build_volume_h16_kernel<true, false>), g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
-                 disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
-    else if (build_variant() == 3)
-      CER_LAUNCH(KK_BUILD, (build_volume_h16_kernel<false, true>), g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj,
-                 n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
-    else
-      CER_LAUNCH(KK_BUILD, (build_volume_h16_kernel<false, false>), g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj,
-                 n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
-  } else if (feats_f16)
-    CER_LAUNCH(KK_BUILD, build_volume_kernel<__half>, grid, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs, disp_in,
-               shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
-  else
-    CER_LAUNCH(KK_BUILD, build_volume_kernel<float>, grid, 256, 0, stream, (const float*)feats, Pij, ii, jj, n_pairs, disp_in,
-               shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+    CER_LAUNCH(KK_BUILD, build_volume_h16_kernel, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
+               disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
+  } else {
+    const int chunks = ceil_div(D, 8);
+    dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));
+    CER_LAUNCH(KK_BUILD, build_volume_kernel<float>, grid, 256, 0, stream, (const float*)feats, Pij, ii, jj, n_pairs,
+               disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w);
+  }
   return check_launch("cer_build_volume");
 }

@@ -76,9 +76,6 @@ int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const i
                      float* origin, float* volume, float out_scale, int per_view, int h, int w,
                      cer_stream_t stream);
 
-/* Kernel used for fp16 features: 0 = 4-lane gather with 256-bit loads + FHFMA mixed-precision FMA (default),
- * 2 = the same with 8 lanes x 128-bit loads (CER_BUILD=l8), 1 = cp.async gather into UMMA tiles + tcgen05.mma
- * (needs D >= 43; CER_BUILD=tc).  fp32 features always use the 8-lane kernel with plain FFMA. */
 /* The same for image rows [y_begin, y_end) only (y_begin a multiple of 8; fp16 features, default kernel): a caller that
  * shards source views over GPUs all-reduces one band of the partial volume while the next band is built. */
 int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
@@ -86,12 +83,14 @@ int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, co
                           float* origin, float* volume, float out_scale, int per_view, int h, int w, int y_begin,
                           int y_end, cer_stream_t stream);
 
+/* Kernel used for fp16 features (cer_build_volume / cer_build_volume_rows and the plan):
+ *   0 = shared-memory-staged source boxes: TMA tensor loads of the epipolar bounding box of a 16 x 8 pixel tile and a
+ *       chunk of hypotheses, tile-vs-box dots on tcgen05.mma, bilinear blend of correlation scalars (default;
+ *       csrc/build_volume_tc.cu);
+ *   1 = L1 row gather, 4 lanes per pixel, 256-bit loads + FHFMA (CER_BUILD=gather; csrc/build_volume.cu).
+ * Both restate core/corr.py:46-97 + alt_cuda_corr.forward (radius 0); they differ in the summation order of the
+ * 64-channel dot only.  fp32 features always use the generic gather kernel with plain FFMA. */
 int cer_set_build_variant(int variant);
-
-/* Corner-dot reuse between consecutive hypotheses in the FHFMA build kernel (fp16 features): 0 = never (default:
- * measured slower on B200, see build_volume.cu), 1 = always, -1 = stages without origin shift only.  Results are
- * bit-identical; only the number of corner rows fetched through L1 changes (CER_BUILD_REUSE). */
-int cer_set_build_reuse(int mode);
 
 /* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
 int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stream_t stream);
