@@ -1,14 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- depth-maps/sec of the CER-MVS inference hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the hot path (core/raft.py:75-108: 2 cost-volume builds + 16+16 GRU
-iterations) over one synthetic DTU-shaped reference image (1184x1600, 10 source views, fp16
-features; BASELINE.json configs[1]).  One process per GPU; at N > 1 every rank works on its own
-reference image (replicas, weak scaling, no data-path collective), and the view-sharded single-image
-path (one NCCL all-reduce of the partial cost volume per stage) is timed next to it.
+A step = one pass of the HOT PATH ONLY (core/raft.py:75-108: 2 cost-volume builds + 16+16 GRU iterations; the
+encoders fnet / cnet of core/extractor.py are NOT part of it, their feature / context maps are the inputs) over one
+synthetic reference image of the chosen BASELINE.json configuration:
+
+    cfg2 (default)  DTU 1184x1600, 10 source views                     -- the configuration the metric is quoted on
+    cfg3            DTU cascaded two-pass: cfg2 + the rescale=2 pass (2368x3200, 592x800 grid) + disp -> depth +
+                    multires merge (multires.py:24-28) per step
+    cfg4            Tanks&Temples 1056x1920, 15 source views           -- at N > 1 ONE image sharded over the N GPUs
+    cfg5            BlendedMVS 1536x2048, 7 source views               -- at N > 1 ONE image sharded over the N GPUs
+
+One process per GPU.  cfg2 / cfg3 at N > 1: every rank works on its own reference image (replicas, weak scaling, no
+data-path collective); the sharded single-image path (every rank builds its run of (view, hypothesis) units, ONE NCCL
+all-reduce of the partial cost volume per stage) is timed next to it at every N.  cfg4 / cfg5 at N > 1: the sharded
+path IS the headline (strong scaling), as BASELINE.json words those configurations.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own Python (baseline/_ref, imported
 unmodified; its CUDA-only alt_cuda_corr.forward served by the oracle's CPU restatement) on all host threads on a
@@ -31,10 +40,27 @@ import torch  # noqa: E402
 
 from cer_mvs_b200 import synth  # noqa: E402
 
-H, W, V = 1184, 1600, 10                  # BASELINE.json configs[1]
 CASCADE = [(64, 64, 16), (-1, 320, 16)]   # "32 iters": 16 + 16 (reference default is 8 + 8, core/raft.py:16)
-WORKLOAD = "DTU 1184x1600 (296x400 grid), 10 source views, 16+16 GRU iterations, fp16 features (BASELINE configs[1])"
+CASCADE_8 = [(64, 64, 8), (-1, 320, 8)]
+CONFIGS = {
+    # name: (H, W, V, sharded headline at N > 1, description)
+    "cfg2": (1184, 1600, 10, False, "DTU 1184x1600 (296x400 grid), 10 source views (BASELINE configs[1])"),
+    "cfg3": (1184, 1600, 10, False, "DTU cascaded two-pass: 1184x1600 + rescale=2 pass 2368x3200 (592x800 grid), 10 source "
+                                    "views, disp->depth + multires merge per step (BASELINE configs[2])"),
+    "cfg4": (1056, 1920, 15, True, "Tanks&Temples 1056x1920 (264x480 grid), 15 source views (BASELINE configs[3])"),
+    "cfg5": (1536, 2048, 7, True, "BlendedMVS 1536x2048 (384x512 grid), 7 source views (BASELINE configs[4])"),
+}
+H, W, V = CONFIGS["cfg2"][:3]
+SCOPE = "HOT PATH ONLY (cost-volume builds + GRU lookup/update iterations, core/raft.py:75-108); encoders excluded, their " \
+        "fp16 feature / context maps are the inputs"
 METRIC = "depth-maps/sec (DTU 1600x1184, 10 src views, 32 iters)"
+
+
+def workload_name(cfg):
+    return f"{CONFIGS[cfg][4]}, 16+16 GRU iterations, fp16 features; {SCOPE}"
+
+
+WORKLOAD = workload_name("cfg2")
 
 
 def peaks():
@@ -149,8 +175,8 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------
-def algorithmic(px):
-    """Algorithmic work per launch of each kernel class (DESIGN.md section 5)."""
+def algorithmic(px, n_views):
+    """Algorithmic work per launch of each kernel class (DESIGN.md section 3)."""
     return {
         "conv_gates": ("tensor", 2.0 * px * 9 * 64 * (241 + 241 + 177)),
         "conv_q_gru": ("tensor", 2.0 * px * 9 * 64 * 64),
@@ -160,13 +186,40 @@ def algorithmic(px):
         # lookup: disp + origin + 3 windows of 12 floats read, 33 floats written = 284 B / pixel
         "lookup": ("hbm", 284.0 * px),
         # fused build per stage: (V+1) feature maps fp16 + disp + volume write; D averaged over the two stages
-        "volume_build": ("hbm", (V + 1) * px * 64 * 2.0 + 4.0 * px + 4.0 * px * (64 + 44) / 2),
+        "volume_build": ("hbm", (n_views + 1) * px * 64 * 2.0 + 4.0 * px + 4.0 * px * (64 + 44) / 2),
     }
+
+
+class Scene:
+    """Pinned host inputs + device copies of one synthetic reference image."""
+
+    def __init__(self, Hh, Ww, Vv, seed, dev):
+        t = torch.from_numpy
+        sc = synth.make_scene(Hh, Ww, Vv, seed=seed)
+        self.H, self.W, self.V = Hh, Ww, Vv
+        self.h1, self.w1 = Hh // 4, Ww // 4
+        self.np_poses, self.np_K = sc["poses"], sc["intrinsics"]
+        self.h_fm = t(sc["fmaps"]).half().pin_memory()
+        self.h_net = t(sc["net"]).half().pin_memory()
+        self.h_inp = t(sc["inp"]).half().pin_memory()
+        self.d_fm, self.d_net, self.d_inp = self.h_fm.to(dev), self.h_net.to(dev), self.h_inp.to(dev)
+        self.d_poses, self.d_K = t(sc["poses"]).to(dev), t(sc["intrinsics"]).to(dev)
+        self.sc = sc
+
+    @property
+    def h2d_bytes(self):
+        return (self.h_fm.numel() + self.h_net.numel() + self.h_inp.numel()) * 2 + (self.V + 1) * (16 + 9) * 4
+
+    def dev_args(self):
+        return (self.d_fm, self.d_net, self.d_inp, self.d_poses, self.d_K, 1.0)
+
+    def host_args(self):
+        return (self.h_fm, self.h_net, self.h_inp, self.np_poses, self.np_K, 1.0)
 
 
 def run_ours(args):
     import torch.distributed as dist
-    from cer_mvs_b200 import _lib
+    from cer_mvs_b200 import _lib, prep
     from cer_mvs_b200.hotpath import DepthHotPath
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,27 +231,43 @@ def run_ours(args):
     _lib.check(_lib.lib().cer_device_check(), "device check")
     if args.conv_variant is not None:
         _lib.check(_lib.lib().cer_set_conv_variant(args.conv_variant), "conv variant")
+    if args.build_variant is not None:
+        _lib.check(_lib.lib().cer_set_build_variant(args.build_variant), "build variant")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    h1, w1 = H // 4, W // 4
+    cfg = args.config
+    Hc, Wc, Vc, sharded_headline, _ = CONFIGS[cfg]
+    sharded_headline = sharded_headline and world > 1
+    two_pass = cfg == "cfg3"
+    h1, w1 = Hc // 4, Wc // 4
     px = h1 * w1
-
-    sc = synth.make_scene(H, W, V, seed=rank)
     sd = synth.make_update_weights(seed=0, delta_scale=0.1, delta_bias=0.005)
-    t = torch.from_numpy
-    h_fm = t(sc["fmaps"]).half().pin_memory()
-    h_net = t(sc["net"]).half().pin_memory()
-    h_inp = t(sc["inp"]).half().pin_memory()
-    h_out = torch.empty(1, 1, h1, w1).pin_memory()
-    d_fm, d_net, d_inp = h_fm.to(dev), h_net.to(dev), h_inp.to(dev)
-    d_poses, d_K = t(sc["poses"]).to(dev), t(sc["intrinsics"]).to(dev)
 
-    hp = DepthHotPath(h1, w1, max_views=V, cascade=CASCADE, feats_f16=True, use_graph=not args.profile_step)
+    # replicas: every rank its own image; sharded headline: every rank the same image
+    scene = Scene(Hc, Wc, Vc, 0 if sharded_headline else rank, dev)
+    hp = DepthHotPath(h1, w1, max_views=Vc, cascade=CASCADE, feats_f16=True, use_graph=not args.profile_step)
     hp.load_update_block(sd)
+    scene2 = hp2 = None
+    if two_pass:                      # the rescale=2 pass: an independent full inference at twice the image size
+        scene2 = Scene(2 * Hc, 2 * Wc, Vc, rank, dev)
+        hp2 = DepthHotPath(2 * h1, 2 * w1, max_views=Vc, cascade=CASCADE, feats_f16=True)
+        hp2.load_update_block(sd)
+
+    def step_device():
+        if sharded_headline:
+            return hp.forward_sharded(*scene.dev_args())
+        out = hp(*scene.dev_args())
+        if two_pass:                  # demo.py:27-43: inference(rescale=1), inference(rescale=2), multires()
+            out2 = hp2(*scene2.dev_args())
+            d1 = prep.disp_to_depth(out.view(h1, w1))
+            d2 = prep.disp_to_depth(out2.view(2 * h1, 2 * w1))
+            return prep.multires_merge(d1, d2, 0.02)
+        return out
+
     if args.profile_step:       # for ncu: W warm-up steps, then exactly one eager step, nothing else
         for _ in range(args.warmup + 1):
-            hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+            step_device()
         torch.cuda.synchronize()
         print(json.dumps({"profile_step": True, "launches_per_step": hp.last_launch_count}))
         return
@@ -215,114 +284,166 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # ---- device-resident throughput (value) ----
     clocks = ClockSampler(local)
     clocks.start()
     for _ in range(args.warmup):
-        hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+        step_device()
     barrier()
     clocks.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+        step_device()
     e1.record()
     barrier()
     clocks.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop()
-    launches = hp.last_launch_count * args.steps
-    value = world * args.steps / (ms / 1e3)
+    launches_per_step = hp.last_launch_count + (hp2.last_launch_count + 3 if two_pass else 0)
+    launches = launches_per_step * args.steps
+    jobs = 1 if sharded_headline else world          # depth maps finished per step over all ranks
+    value = jobs * args.steps / (ms / 1e3)
 
     # ---- the reference's default iteration count, 8 + 8 (core/raft.py:16), device-resident, for SURVEY 8d ----
-    hp8 = DepthHotPath(h1, w1, max_views=V, cascade=[(64, 64, 8), (-1, 320, 8)], feats_f16=True)
-    hp8.load_update_block(sd)
-    for _ in range(args.warmup):
-        hp8(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
-    barrier()
-    n8 = max(args.steps // 2, 3)
-    e0.record()
-    for _ in range(n8):
-        hp8(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
-    e1.record()
-    barrier()
-    ms8 = max_over_ranks(e0.elapsed_time(e1)) / n8
-    del hp8
+    ms8 = None
+    if cfg == "cfg2":
+        hp8 = DepthHotPath(h1, w1, max_views=Vc, cascade=CASCADE_8, feats_f16=True)
+        hp8.load_update_block(sd)
+        n8 = max(args.steps // 2, 3)
+        ms8 = timed(lambda: hp8(*scene.dev_args()), n8, args.warmup) / n8
+        del hp8
 
     # ---- end to end with host buffers (e2e): every step copies its inputs from pinned host memory and reads its
-    # disparity back; the copies of step i+1 overlap the kernels of step i (cer_plan_submit_host, two jobs in flight) ----
-    h_outs = [torch.empty(1, 1, h1, w1).pin_memory() for _ in range(2)]
-    for i in range(min(args.warmup, 2)):
-        hp.submit_host(h_fm, h_net, h_inp, sc["poses"], sc["intrinsics"], 1.0, out=h_outs[i & 1])
-    hp.wait_host()
-    hp.wait_host()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        hp.submit_host(h_fm, h_net, h_inp, sc["poses"], sc["intrinsics"], 1.0, out=h_outs[i & 1])
-        if i >= 1:
-            hp.wait_host()            # result of step i-1 is on the host
-    hp.wait_host()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    # latency of one synchronous call (copies not overlapped), for reference
-    t0 = time.perf_counter()
-    for _ in range(3):
-        hp.run_host(h_fm, h_net, h_inp, sc["poses"], sc["intrinsics"], 1.0, out=h_out)
-    sync_ms = 1e3 * (time.perf_counter() - t0) / 3
-    h2d = h_fm.numel() * 2 + h_net.numel() * 2 + h_inp.numel() * 2 + (V + 1) * (16 + 9) * 4
-    d2h = px * 4
-    e2e = world * args.steps / e2e_s
+    # result back ----
+    h2d = scene.h2d_bytes + (scene2.h2d_bytes if two_pass else 0)
+    d2h = (4 * px if two_pass else px) * 4
+    sync_ms = None
+    if not sharded_headline and not two_pass:
+        # the copies of step i+1 overlap the kernels of step i (cer_plan_submit_host, two jobs in flight)
+        h_outs = [torch.empty(1, 1, h1, w1).pin_memory() for _ in range(2)]
+        for i in range(min(args.warmup, 2)):
+            hp.submit_host(*scene.host_args(), out=h_outs[i & 1])
+        hp.wait_host()
+        hp.wait_host()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            hp.submit_host(*scene.host_args(), out=h_outs[i & 1])
+            if i >= 1:
+                hp.wait_host()            # result of step i-1 is on the host
+        hp.wait_host()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        t0 = time.perf_counter()
+        h_out = torch.empty(1, 1, h1, w1).pin_memory()
+        for _ in range(3):               # latency of one synchronous call (copies not overlapped), for reference
+            hp.run_host(*scene.host_args(), out=h_out)
+        sync_ms = 1e3 * (time.perf_counter() - t0) / 3
+        e2e_api = "cer_plan_submit_host / cer_plan_wait_host (pinned host buffers, 2 jobs in flight)"
+    else:
+        # sharded / two-pass: explicit pinned -> device copies on the stream, the public device API, result back to a
+        # pinned host buffer; one synchronisation per step
+        scenes = [scene] + ([scene2] if two_pass else [])
+        h_res = torch.empty((2 * h1, 2 * w1) if two_pass else (1, 1, h1, w1)).pin_memory()
+
+        def step_host():
+            for sc_ in scenes:
+                sc_.d_fm.copy_(sc_.h_fm, non_blocking=True)
+                sc_.d_net.copy_(sc_.h_net, non_blocking=True)
+                sc_.d_inp.copy_(sc_.h_inp, non_blocking=True)
+                sc_.d_poses.copy_(torch.from_numpy(sc_.np_poses), non_blocking=False)
+                sc_.d_K.copy_(torch.from_numpy(sc_.np_K), non_blocking=False)
+            out = step_device()
+            h_res.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_api = ("DepthHotPath.forward_sharded" if sharded_headline else "DepthHotPath x2 + prep.multires_merge") + \
+                  " on device tensors; pinned host -> device copies and the result read-back inside every step"
+    e2e = jobs * args.steps / e2e_s
 
     # ---- per-kernel breakdown with CUDA events (eager), roofline of the dominant kernel ----
     hp.set_kernel_timing(True)
-    hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+    hp(*scene.dev_args())
     hp.kernel_times()
     ksteps = min(args.steps, 5)
     for _ in range(ksteps):
-        hp(d_fm, d_net, d_inp, d_poses, d_K, 1.0)
+        hp(*scene.dev_args())
     kt = hp.kernel_times()
     hp.set_kernel_timing(False)
     pk = peaks()
-    alg = algorithmic(px)
+    alg = algorithmic(px, Vc)
     kernels = {}
     for k, (tot, n) in kt.items():
         if n == 0:
             continue
+        if k == "volume_build":       # one build per cascade stage = the staged kernel + the gather pass for flagged tiles
+            n = 2 * ksteps
         ent = {"ms_per_step": tot / ksteps, "launches_per_step": n / ksteps, "avg_us": 1e3 * tot / n}
         if k in alg:
             bound, work = alg[k]
             ach = work / (tot / n * 1e-3) / (1e9 if bound == "hbm" else 1e12)
             ent.update(bound=bound, achieved=ach, frac=ach / pk[bound], unit="GB/s" if bound == "hbm" else "TFLOP/s")
         kernels[k] = ent
+    ksum = sum(v["ms_per_step"] for v in kernels.values())
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from an ncu --set full capture
+    tjson = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from ncu --set full captures
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get(dom)
-    roof = {"kernel": dom, "bound": kernels[dom].get("bound"), "achieved": kernels[dom].get("achieved"),
-            "peak": pk.get(kernels[dom].get("bound", "tensor")), "unit": kernels[dom].get("unit"),
-            "frac": kernels[dom].get("frac"), "traffic": traffic, "peak_source": pk["src"],
-            "avg_launch_us": kernels[dom]["avg_us"], "share_of_step": kernels[dom]["ms_per_step"] /
-            sum(v["ms_per_step"] for v in kernels.values())}
+        tjson = json.load(open(tp))
+
+    def roof_of(k):
+        return {"kernel": k, "bound": kernels[k].get("bound"), "achieved": kernels[k].get("achieved"),
+                "peak": pk.get(kernels[k].get("bound", "tensor")), "unit": kernels[k].get("unit"),
+                "frac": kernels[k].get("frac"), "traffic": tjson.get(k) if cfg == "cfg2" else None,
+                "peak_source": pk["src"], "avg_launch_us": kernels[k]["avg_us"],
+                "share_of_step": kernels[k]["ms_per_step"] / ksum,
+                "share_note": "share of the SUM of event-timed kernels of an eager pass (an event pair adds ~6 us to "
+                              "every short launch, so the sum exceeds the graph-replayed ms_per_step)"}
+    roof = roof_of(dom)
+    build_roof = roof_of("volume_build") if "volume_build" in kernels else None
+    if build_roof is not None:
+        build_roof["note"] = ("algorithmic HBM bytes; the kernel's real bound is arithmetic: 512 flop per sample "
+                              "(px * D * V samples) = %.1f GFLOP per launch on average" %
+                              (512.0 * px * Vc * 54 / 1e9))
+    lookup_plan_roof = roof_of("lookup") if "lookup" in kernels else None
 
     # ---- the stand-alone correlation-lookup kernel (CorrBlock.__call__ drop-in, cer_lookup) on per-view volumes:
-    # slots = V, so one launch moves V * px * (4 D + 8 + 132) bytes (303 MB of volume: larger than L2, nothing is
-    # reused between launches); algorithmic bytes per SURVEY 8d = slots * px * 284 ----
+    # slots = V, so one launch moves V * px * (4 D + 8 + 132) bytes (larger than L2, nothing is reused between
+    # launches); algorithmic bytes per SURVEY 8d = slots * px * 284 ----
     lookup_roof = None
-    if rank == 0:
+    if rank == 0 and cfg == "cfg2":
         L = _lib.lib()
         Dl, incre = 64, 0.0025 / 64
         g = torch.Generator(device=dev).manual_seed(1)
-        vol = torch.randn(V, px, Dl, device=dev, generator=g)
+        vol = torch.randn(Vc, px, Dl, device=dev, generator=g)
         origin = torch.full((px,), 32 * incre, device=dev)
         zinv = origin + (torch.rand(px, device=dev, generator=g) * 40 - 20) * incre
-        lout = torch.empty(V, 33, px, device=dev)
+        lout = torch.empty(Vc, 33, px, device=dev)
         st = _lib.stream_ptr()
 
         def run_lookup():
-            _lib.check(L.cer_lookup(vol.data_ptr(), V, origin.data_ptr(), zinv.data_ptr(), Dl, incre, 5, 3,
+            _lib.check(L.cer_lookup(vol.data_ptr(), Vc, origin.data_ptr(), zinv.data_ptr(), Dl, incre, 5, 3,
                                     lout.data_ptr(), h1, w1, st), "cer_lookup")
         for _ in range(3):
             run_lookup()
@@ -334,38 +455,34 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / n_l
-        alg_b, moved_b = V * px * 284.0, V * px * (4.0 * Dl + 8 + 132)
+        alg_b, moved_b = Vc * px * 284.0, Vc * px * (4.0 * Dl + 8 + 132)
         lookup_roof = {"kernel": "lookup_v2_kernel<64> (cer_lookup, slots = V per-view volumes)", "bound": "hbm",
                        "achieved": alg_b / (us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                        "frac": alg_b / (us * 1e-6) / 1e9 / pk["hbm"], "avg_launch_us": us,
                        "design_bytes_per_launch": moved_b, "design_gbs": moved_b / (us * 1e-6) / 1e9,
                        "design_frac": moved_b / (us * 1e-6) / 1e9 / pk["hbm"],
                        "note": "rows are read whole (4D+8 B in, 132 B out per pixel-slot = 396 B at D=64), so 284 "
-                               "algorithmic bytes cap 'frac' at 0.72 of the achieved HBM fraction ('design_frac')"}
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes of this launch from the ncu capture
-        lookup_roof["traffic"] = json.load(open(tpath)).get("lookup_dropin_slotsV") if os.path.isfile(tpath) else None
+                               "algorithmic bytes cap 'frac' at 0.72 of the achieved HBM fraction ('design_frac')",
+                       "traffic": tjson.get("lookup_dropin_slotsV"),
+                       "in_plan_kernel": lookup_plan_roof}
         del vol, lout
 
-    # ---- view-sharded single image (NCCL all-reduce of the partial volume per stage) ----
-    viewshard = None
-    if world > 1 and world <= V:
-        sc0 = sc if rank == 0 else synth.make_scene(H, W, V, seed=0)
-        f0, n0, i0 = t(sc0["fmaps"]).half().to(dev), t(sc0["net"]).half().to(dev), t(sc0["inp"]).half().to(dev)
-        p0, k0 = t(sc0["poses"]).to(dev), t(sc0["intrinsics"]).to(dev)
-        for _ in range(3):
-            hp.forward_view_sharded(f0, n0, i0, p0, k0, 1.0)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            hp.forward_view_sharded(f0, n0, i0, p0, k0, 1.0)
-        e1.record()
-        barrier()
-        vms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        viewshard = {"ms_per_depth_map": vms, "depth_maps_per_s": 1e3 / vms, "collective": "nccl all_reduce(sum) of "
-                     f"the partial volume, {px * 64 * 4 / 1e6:.1f}+{px * 44 * 4 / 1e6:.1f} MB per depth map"}
+    # ---- one image sharded over all ranks (NCCL all-reduce of the partial volume per stage), at every N > 1 ----
+    sharded = None
+    if world > 1 and not sharded_headline and not two_pass:
+        sc0 = scene if rank == 0 else Scene(Hc, Wc, Vc, 0, dev)
+        vms = timed(lambda: hp.forward_sharded(*sc0.dev_args()), args.steps, 3) / args.steps
+        sharded = {"ms_per_depth_map": vms, "depth_maps_per_s": 1e3 / vms,
+                   "units": f"{Vc} views x (64 | 44) hypotheses split evenly over {world} ranks",
+                   "collective": "nccl all_reduce(sum) of the partial volume, "
+                                 f"{px * 64 * 4 / 1e6:.1f}+{px * 44 * 4 / 1e6:.1f} MB per depth map"}
+    elif sharded_headline:
+        # ... and the replica mode next to the sharded headline
+        rms = timed(lambda: hp(*scene.dev_args()), args.steps, 3) / args.steps
+        sharded = {"replicas_depth_maps_per_s": world * 1e3 / rms, "replicas_ms_per_depth_map": rms}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and cfg == "cfg2":
         # one bounded sample of ~10-20 s of CPU work: 24 of 296 rows, 1+1 iterations
         cores = host_threads()
         full, desc, kind = cpu_sample(rows=3 * args.ref_rows, iters=(1, 1))
@@ -373,22 +490,22 @@ def run_ours(args):
 
     # ---- the reference's GPU path on this same B200: its Python, its kernel, real autocast ----
     ref_gpu = None
-    if rank == 0 and world == 1 and not args.no_reference_gpu:
+    if rank == 0 and world == 1 and not args.no_reference_gpu and cfg == "cfg2":
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         try:
             import bench_ref
             import refrun
             if refrun.available("gpu"):
-                r = bench_ref.reference_gpu(H, W, V, sc, sd, {"16+16": CASCADE, "8+8": [(64, 64, 8), (-1, 320, 8)]}, dev)
+                r = bench_ref.reference_gpu(Hc, Wc, Vc, scene.sc, sd, {"16+16": CASCADE, "8+8": CASCADE_8}, dev)
                 ref_gpu = {
                     "what": "UNMODIFIED reference on this GPU: core/raft.py:75-108 with its own CorrBlock / UpdateBlock, "
                             "its own alt_cuda_corr kernel (sm_100 build), torch.cuda.amp.autocast; stub encoders; "
                             "inputs resident; CUDA events",
                     "ms_per_depth_map_16_16": r["16+16"], "depth_maps_per_s_16_16": 1e3 / r["16+16"],
                     "ms_per_depth_map_8_8": r["8+8"], "depth_maps_per_s_8_8": 1e3 / r["8+8"],
-                    "speedup_16_16": (ms / args.steps) and r["16+16"] / (ms / args.steps),
-                    "speedup_8_8": r["8+8"] / ms8, "north_star_target": ">= 4x",
-                    "corr_kernels": bench_ref.corr_kernel_legs(H, W, V, sc, dev),
+                    "speedup_16_16": r["16+16"] / (ms / args.steps),
+                    "speedup_8_8": r["8+8"] / ms8 if ms8 else None, "north_star_target": ">= 4x",
+                    "corr_kernels": bench_ref.corr_kernel_legs(Hc, Wc, Vc, scene.sc, dev),
                 }
             else:
                 ref_gpu = {"unavailable": "baseline/_ref or oracle/_ref did not travel"}
@@ -396,24 +513,31 @@ def run_ours(args):
             ref_gpu = {"unavailable": repr(e)[:300]}
 
     if rank == 0:
+        if sharded_headline:
+            par, scaling = f"one image sharded over {world} GPUs ((view, hypothesis) units, 1 NCCL all-reduce per stage)", "strong"
+        else:
+            par, scaling = (f"replicas x{world}" if world > 1 else "single GPU"), "weak"
         line = {
-            "metric": METRIC, "value": value, "unit": "depth-maps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC if cfg == "cfg2" else f"depth-maps/sec ({CONFIGS[cfg][4]}, 32 iters)",
+            "value": value, "unit": "depth-maps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: 167 MB fp16 feature maps + 30 MB volume + 110 MB update "
-                             "workspace are re-streamed every step (L2 = 126 MB)",
-                       "engine": "cer_plan, CUDA graph per cascade stage"},
+            "config": {"workload": workload_name(cfg), "parallelism": par,
+                       "l2": "inputs larger than L2: fp16 feature maps (%d MB) + cost volume + update workspace are "
+                             "re-streamed every step (L2 = 126 MB)" % ((Vc + 1) * px * 128 // 1000000),
+                       "engine": "cer_plan, CUDA graph per cascade stage",
+                       "scope": SCOPE},
             "e2e": {"value": e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "sync_call_ms": sync_ms,
-                    "api": "cer_plan_submit_host / cer_plan_wait_host (pinned host buffers, 2 jobs in flight)"},
-            "gpu_launches": launches, "iters_8_8": {"value": world * 1e3 / ms8, "unit": "depth-maps/s", "ms_per_step": ms8,
-                                                  "note": "same workload with the reference's default 8+8 iterations"},
-            "clocks": clk, "roofline": roof, "lookup_roofline": lookup_roof,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "sync_call_ms": sync_ms, "api": e2e_api},
+            "gpu_launches": launches,
+            "clocks": clk, "roofline": roof, "build_roofline": build_roof, "lookup_roofline": lookup_roof,
             "cpu_baseline": cpu, "reference_gpu": ref_gpu, "kernels": kernels,
         }
-        if viewshard:
-            line["viewshard"] = viewshard
+        if ms8:
+            line["iters_8_8"] = {"value": world * 1e3 / ms8, "unit": "depth-maps/s", "ms_per_step": ms8,
+                                 "note": "same workload with the reference's default 8+8 iterations"}
+        if sharded:
+            line["sharded" if not sharded_headline else "replicas"] = sharded
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -430,6 +554,8 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-this-GPU leg")
     ap.add_argument("--profile-step", action="store_true", help="ncu helper: warm-up + one eager step only")
     ap.add_argument("--conv-variant", type=int, default=None, help="cer_set_conv_variant (A/B experiments)")
+    ap.add_argument("--build-variant", type=int, default=None, help="cer_set_build_variant (A/B experiments)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

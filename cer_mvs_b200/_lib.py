@@ -27,10 +27,11 @@ SIGNATURES = {
     "cer_projection_matrices": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "cer_build_volume": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                  c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p]),
-    "cer_build_volume_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+    "cer_build_volume_part": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                       c_float, c_float, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
-                                      c_void_p]),
+                                      c_int, c_void_p]),
     "cer_set_build_variant": (c_int, [c_int]),
+    "cer_debug_set_build_profile": (c_int, [c_void_p]),
     "cer_pool_pairs": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "cer_lookup": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_int,
                            c_int, c_void_p]),
@@ -44,8 +45,6 @@ SIGNATURES = {
     "cer_geometric_filter": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_double, c_double] + [c_void_p] * 10),
     "cer_set_conv_variant": (c_int, [c_int]),
     "cer_set_lookup_variant": (c_int, [c_int]),
-    "cer_set_tile_flags": (c_int, [c_int]),
-    "cer_set_conv_a_tma": (c_int, [c_int]),
     "cer_debug_set_conv_profile": (c_int, [c_void_p]),
     "cer_gru_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
     "cer_update_blob_bytes": (c_size_t, []),
@@ -66,7 +65,7 @@ SIGNATURES = {
     "cer_plan_prepare": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_void_p]),
     "cer_plan_build_stage": (c_int, [c_void_p, c_int, c_void_p]),
-    "cer_plan_build_stage_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cer_plan_build_stage_units": (c_int, [c_void_p, c_int, c_ll, c_ll, c_void_p]),
     "cer_plan_partial_volume": (c_void_p, [c_void_p, c_int, C.POINTER(c_size_t)]),
     "cer_plan_iterate_stage": (c_int, [c_void_p, c_int, c_void_p]),
     "cer_plan_finish": (c_int, [c_void_p, c_float, c_void_p, c_void_p]),

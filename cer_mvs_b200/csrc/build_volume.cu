@@ -250,7 +250,12 @@ __global__ void __launch_bounds__(256, 4) build_volume_h16_kernel(
     const __half* __restrict__ feats, const float* __restrict__ Pij, const int* __restrict__ ii,
     const int* __restrict__ jj, int n_pairs, const float* __restrict__ disp_in, int shift, int D, float incre,
     float lo_origin, float* __restrict__ origin_out, float* __restrict__ volume, float out_scale, int per_view,
-    int h, int w, int y_begin) {
+    int h, int w, int y_begin, int d_begin, int d_end, int accumulate, const int* __restrict__ tile_only) {
+  // second pass behind the staged kernel: only the 16 x 8 tiles it flagged (this block's 8 x 8 tile is half of one)
+  if (tile_only != nullptr) {
+    const int tx8 = (w + 7) >> 3, tx16 = (w + 15) >> 4;
+    if (tile_only[(blockIdx.y / tx8) * tx16 + ((blockIdx.y % tx8) >> 1)] == 0) return;
+  }
   __shared__ float sP[kMaxPairs][12];
   __shared__ int sI[kMaxPairs], sJ[kMaxPairs];
   // per 4-lane group: 4 samples x {4 byte offsets, 4 weights} = 32 words, padded to 36: a quarter-warp (two groups)
@@ -285,8 +290,8 @@ __global__ void __launch_bounds__(256, 4) build_volume_h16_kernel(
 
   const int chunk0 = blockIdx.x * kH16Chunks;
   for (int ch = chunk0; ch < chunk0 + kH16Chunks; ++ch) {
-    const int d0 = ch * 4;
-    if (d0 >= D) break;
+    const int d0 = d_begin + ch * 4;
+    if (d0 >= d_end) break;
     const int d = d0 + lane;
     const float dval = __fadd_rn(__fmul_rn((float)(min(d, D - 1) - D / 2), incre), org);   // corr.py:56,66
     float acc = 0.f;
@@ -351,12 +356,18 @@ __global__ void __launch_bounds__(256, 4) build_volume_h16_kernel(
       const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
       const float total = ((lane & 1) ? k2[1] : k2[0]) + recv;
       if (per_view) {
-        if (valid && d < D) volume[((long long)k * px + p) * D + d] = total * out_scale;
+        if (valid && d < d_end) {
+          float* o = volume + ((long long)k * px + p) * D + d;
+          *o = accumulate ? *o + total * out_scale : total * out_scale;
+        }
       } else {
         acc += total;
       }
     }
-    if (!per_view && valid && d < D) volume[p * D + d] = acc * out_scale;
+    if (!per_view && valid && d < d_end) {
+      float* o = volume + p * D + d;
+      *o = accumulate ? *o + acc * out_scale : acc * out_scale;
+    }
   }
 }
 
@@ -365,8 +376,8 @@ __global__ void __launch_bounds__(256, 4) build_volume_h16_kernel(
 namespace cer {
 int build_volume_tc(const void* feats, const float* Pij, const int* ii, const int* jj, int n_pairs,
                     const float* disp_in, int shift, int D, float incre, float lo_origin, float* origin,
-                    float* volume, float out_scale, int per_view, int h, int w, int y_begin, int y_end,
-                    cudaStream_t stream);
+                    float* volume, float out_scale, int per_view, int h, int w, int y_begin, int y_end, int d_begin,
+                    int d_end, int accumulate, int** tile_skip_out, cudaStream_t stream);
 // 0 = shared-memory-staged source boxes + tcgen05 (build_volume_tc.cu, default for fp16 features);
 // 1 = L1 row gather with FHFMA (this file).  fp32 features always take the generic gather kernel.
 static int g_build_variant = -1;
@@ -381,6 +392,15 @@ static int build_variant() {
 
 using namespace cer;
 
+namespace cer {
+void build_set_profile(unsigned long long* dev);
+}
+// Debug: per-role counters of the staged build kernel, 16 x u64 on the device (nullptr switches them off).
+extern "C" int cer_debug_set_build_profile(unsigned long long* dev_counters) {
+  cer::build_set_profile(dev_counters);
+  return CER_OK;
+}
+
 extern "C" int cer_set_build_variant(int variant) {
   CER_REQUIRE(variant >= 0 && variant <= 1,
               "cer_set_build_variant: 0 TMA-staged source boxes + tcgen05 (default); 1 L1 row gather (FHFMA)");
@@ -388,42 +408,48 @@ extern "C" int cer_set_build_variant(int variant) {
   return CER_OK;
 }
 
-extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+extern "C" int cer_build_volume_part(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
                                      int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
                                      float* origin, float* volume, float out_scale, int per_view, int h, int w,
-                                     int y_begin, int y_end, cer_stream_t stream);
+                                     int d_begin, int d_end, int accumulate, cer_stream_t stream);
 
 extern "C" int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
                                 int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
                                 float* origin, float* volume, float out_scale, int per_view, int h, int w,
                                 cer_stream_t stream) {
-  return cer_build_volume_rows(feats, feats_f16, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin,
-                               volume, out_scale, per_view, h, w, 0, h, stream);
+  return cer_build_volume_part(feats, feats_f16, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin,
+                               volume, out_scale, per_view, h, w, 0, D, 0, stream);
 }
 
-// Rows [y_begin, y_end) of the volume only (y_begin a multiple of 8): lets a caller that shards views over GPUs
-// all-reduce one band of the partial volume while the next band is being built.
-extern "C" int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+// Hypotheses [d_begin, d_end) of the given views only, optionally ADDED to the volume: the unit of work of the sharded
+// build (a rank owns a contiguous run of (view, hypothesis) units; partial volumes are summed by one all-reduce).
+extern "C" int cer_build_volume_part(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
                                      int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
                                      float* origin, float* volume, float out_scale, int per_view, int h, int w,
-                                     int y_begin, int y_end, cer_stream_t stream) {
-  CER_REQUIRE(y_begin >= 0 && y_begin < y_end && y_end <= h && (y_begin & 7) == 0,
-              "cer_build_volume_rows: rows [%d, %d) must lie in the image and start on a multiple of 8", y_begin, y_end);
-  const bool whole = y_begin == 0 && y_end == h;
+                                     int d_begin, int d_end, int accumulate, cer_stream_t stream) {
   CER_REQUIRE(feats && Pij && ii && jj && disp_in && origin && volume, "cer_build_volume: null pointer");
   CER_REQUIRE(n_pairs > 0 && n_pairs <= kMaxPairs, "cer_build_volume: n_pairs must be 1..%d", kMaxPairs);
   CER_REQUIRE(D > 0 && h > 0 && w > 0, "cer_build_volume: bad sizes");
+  CER_REQUIRE(d_begin >= 0 && d_begin < d_end && d_end <= D, "cer_build_volume_part: hypotheses [%d, %d) outside 0..%d",
+              d_begin, d_end, D);
   CER_REQUIRE(aligned16(feats), "cer_build_volume: feats must be 16-byte aligned");
-  CER_REQUIRE(whole || feats_f16, "cer_build_volume_rows: row bands need fp16 features");
-  if (feats_f16 && build_variant() == 0 && (reinterpret_cast<uintptr_t>(feats) & 127) == 0)
-    return build_volume_tc(feats, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale,
-                           per_view, h, w, y_begin, y_end, (cudaStream_t)stream);
+  const bool whole = d_begin == 0 && d_end == D && !accumulate;
+  CER_REQUIRE(whole || feats_f16, "cer_build_volume_part: partial / accumulating builds need fp16 features");
   const long long px = (long long)h * w;
+  // fp16 features: the staged tcgen05 kernel first; it flags the tiles whose hypothesis origins are too incoherent for a
+  // common source box, and the gather kernel then computes exactly those (tile_only); CER_BUILD=gather: gather only
+  int* tile_only = nullptr;
+  if (feats_f16 && build_variant() == 0 && (reinterpret_cast<uintptr_t>(feats) & 127) == 0) {
+    int rc = build_volume_tc(feats, Pij, ii, jj, n_pairs, disp_in, shift, D, incre, lo_origin, origin, volume, out_scale,
+                             per_view, h, w, 0, h, d_begin, d_end, accumulate, &tile_only, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   if (feats_f16) {
-    dim3 g16(ceil_div(ceil_div(D, 4), kH16Chunks), ((w + 7) / 8) * ((y_end - y_begin + 7) / 8));
+    dim3 g16(ceil_div(ceil_div(d_end - d_begin, 4), kH16Chunks), ((w + 7) / 8) * ((h + 7) / 8));
     CER_REQUIRE(g16.y <= 65535u, "cer_build_volume: image too large for the tile grid (%u tiles)", g16.y);
     CER_LAUNCH(KK_BUILD, build_volume_h16_kernel, g16, 256, 0, stream, (const __half*)feats, Pij, ii, jj, n_pairs,
-               disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, y_begin);
+               disp_in, shift, D, incre, lo_origin, origin, volume, out_scale, per_view, h, w, 0, d_begin, d_end,
+               accumulate, (const int*)tile_only);
   } else {
     const int chunks = ceil_div(D, 8);
     dim3 grid(ceil_div(px * 8, 256), ceil_div(chunks, kChunksPerBlock));

@@ -61,6 +61,15 @@ __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restri
   if (i < n) dst[i] = src[i] * s;
 }
 
+// hypothesis origin of a stage (core/corr.py:59-63), for ranks of a sharded build that own no unit of it
+__global__ void origin_kernel(const float* __restrict__ disp, int shift, float lo, float* __restrict__ origin, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float d = disp[i];
+    origin[i] = shift ? (d < lo ? lo : d) : d;
+  }
+}
+
 __global__ void iota_pairs_kernel(int* ii, int* jj, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -212,7 +221,7 @@ int cer_plan_prepare(cer_plan* p, const void* fmaps, int fmaps_f16, const void* 
   CER_REQUIRE(p->have_weights, "cer_plan_prepare: call cer_plan_set_weights first");
   CER_REQUIRE(n_views >= 1 && n_views <= p->cfg.max_views, "cer_plan_prepare: n_views %d outside 1..%d", n_views,
               p->cfg.max_views);
-  CER_REQUIRE(view_begin >= 0 && view_begin < view_end && view_end <= n_views, "cer_plan_prepare: bad view range");
+  CER_REQUIRE(view_begin >= 0 && view_begin <= view_end && view_end <= n_views, "cer_plan_prepare: bad view range");
   const int h = p->cfg.h, w = p->cfg.w;
   const long long px = p->px;
   const size_t in_sz = fmaps_f16 ? 2 : 4, f_sz = p->cfg.feats_f16 ? 2 : 4;
@@ -221,14 +230,16 @@ int cer_plan_prepare(cer_plan* p, const void* fmaps, int fmaps_f16, const void* 
   // reference image + the owned source views, scaled by 1/8 (core/corr.py:30-31)
   if ((rc = cer_nchw_to_nhwc(fmaps, fmaps_f16, p->feats, p->cfg.feats_f16, 1, 64, h, w, 0.125f, stream))) return rc;
   const size_t img_in = (size_t)px * 64 * in_sz, img_f = (size_t)px * 64 * f_sz;
-  if ((rc = cer_nchw_to_nhwc((const char*)fmaps + (1 + view_begin) * img_in, fmaps_f16,
+  if (view_end > view_begin &&
+      (rc = cer_nchw_to_nhwc((const char*)fmaps + (1 + view_begin) * img_in, fmaps_f16,
                              (char*)p->feats + (1 + view_begin) * img_f, p->cfg.feats_f16, view_end - view_begin, 64,
                              h, w, 0.125f, stream)))
     return rc;
   if ((rc = cer_nchw_to_nhwc(net, ctx_f16, p->net, 1, 1, 64, h, w, 1.f, stream))) return rc;
   if ((rc = cer_nchw_to_nhwc(inp, ctx_f16, p->inp, 1, 1, 64, h, w, 1.f, stream))) return rc;
   CER_CUDA(cudaMemsetAsync(p->disp, 0, px * 4, (cudaStream_t)stream));   // core/raft.py:52
-  if ((rc = cer_projection_matrices(poses, intrinsics, p->ii + view_begin, p->jj + view_begin,
+  if (view_end > view_begin &&
+      (rc = cer_projection_matrices(poses, intrinsics, p->ii + view_begin, p->jj + view_begin,
                                     view_end - view_begin, p->Pij + view_begin * 16, stream)))
     return rc;
   p->n_views = n_views;
@@ -239,19 +250,65 @@ int cer_plan_prepare(cer_plan* p, const void* fmaps, int fmaps_f16, const void* 
 }
 
 int cer_plan_build_stage(cer_plan* p, int s, cer_stream_t stream) {
-  CER_REQUIRE(p, "cer_plan_build_stage: null plan");
-  return cer_plan_build_stage_rows(p, s, 0, p->cfg.h, stream);
-}
-
-int cer_plan_build_stage_rows(cer_plan* p, int s, int y_begin, int y_end, cer_stream_t stream) {
   CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_build_stage: bad stage");
   const int D = p->cfg.D[s];
   const double incre = (double)p->cfg.incre[s];
   const float lo = (float)((D / 2) * incre);   // torch.tensor(nIncre // 2 * incre).float(), core/corr.py:60
   cer::g_launches = 0;
-  int rc = cer_build_volume_rows(p->feats, p->cfg.feats_f16, p->Pij + p->vb * 16, p->ii + p->vb, p->jj + p->vb,
-                                 p->ve - p->vb, p->disp, s == 0, D, (float)incre, lo, p->origin, p->volume,
-                                 1.f / (float)p->n_views, 0, p->cfg.h, p->cfg.w, y_begin, y_end, stream);
+  int rc = cer_build_volume(p->feats, p->cfg.feats_f16, p->Pij + p->vb * 16, p->ii + p->vb, p->jj + p->vb,
+                            p->ve - p->vb, p->disp, s == 0, D, (float)incre, lo, p->origin, p->volume,
+                            1.f / (float)p->n_views, 0, p->cfg.h, p->cfg.w, stream);
+  p->launches += cer::g_launches;
+  return rc;
+}
+
+// Sharded build: the work of a stage is n_views * D units (view, hypothesis), view-major; a rank
+// builds the contiguous run [unit_begin, unit_end) into a zeroed partial volume -- at most three kernel calls (tail of
+// the first view, whole views, head of the last view), each adding to the volume -- and the partial volumes of all
+// ranks are summed by one all-reduce.  Works for any number of ranks (more ranks than views: cfg 5 of BASELINE.json).
+int cer_plan_build_stage_units(cer_plan* p, int s, long long unit_begin, long long unit_end, cer_stream_t stream) {
+  CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_build_stage_units: bad stage");
+  CER_REQUIRE(p->cfg.feats_f16, "cer_plan_build_stage_units: needs a plan with fp16 features");
+  const int D = p->cfg.D[s];
+  const long long U = (long long)p->n_views * D;
+  CER_REQUIRE(unit_begin >= 0 && unit_begin <= unit_end && unit_end <= U, "cer_plan_build_stage_units: units [%lld, %lld) "
+              "outside 0..%lld", unit_begin, unit_end, U);
+  const double incre = (double)p->cfg.incre[s];
+  const float lo = (float)((D / 2) * incre);
+  cer::g_launches = 0;
+  CER_CUDA(cudaMemsetAsync(p->volume, 0, (size_t)p->px * D * 4, (cudaStream_t)stream));
+  p->launches += 1;
+  int rc = CER_OK;
+  if (unit_end > unit_begin) {
+    const int v0 = (int)(unit_begin / D), a = (int)(unit_begin % D);
+    const int v1 = (int)((unit_end - 1) / D), b = (int)((unit_end - 1) % D) + 1;
+    CER_REQUIRE(v0 >= p->vb && v1 < p->ve, "cer_plan_build_stage_units: views %d..%d were not prepared (prepared %d..%d)",
+                v0, v1, p->vb, p->ve - 1);
+    auto part = [&](int vb, int ve, int d0, int d1) {
+      return cer_build_volume_part(p->feats, 1, p->Pij + vb * 16, p->ii + vb, p->jj + vb, ve - vb, p->disp, s == 0, D,
+                                   (float)incre, lo, p->origin, p->volume, 1.f / (float)p->n_views, 0, p->cfg.h,
+                                   p->cfg.w, d0, d1, 1, stream);
+    };
+    if (v0 == v1) {
+      rc = part(v0, v0 + 1, a, b);
+    } else {
+      int first_whole = v0, last_whole = v1;       // whole views [first_whole, last_whole)
+      if (a > 0) {
+        rc = part(v0, v0 + 1, a, D);
+        first_whole = v0 + 1;
+      }
+      if (b < D) {
+        if (!rc) rc = part(v1, v1 + 1, 0, b);
+      } else {
+        last_whole = v1 + 1;
+      }
+      if (!rc && last_whole > first_whole) rc = part(first_whole, last_whole, 0, D);
+    }
+  } else {
+    // a rank without units still needs the hypothesis origin (every rank runs the lookups)
+    CER_LAUNCH(KK_BUILD, origin_kernel, ceil_div(p->px, 256), 256, 0, stream, p->disp, s == 0, lo, p->origin, p->px);
+    rc = check_launch("cer_plan_build_stage_units (origin)");
+  }
   p->launches += cer::g_launches;
   return rc;
 }

@@ -272,154 +272,7 @@ constexpr int kL2_WARPS = 4;
 constexpr int kL2_P0 = kPyrP0, kL2_P1 = kPyrP1, kL2_P2 = kPyrP2;      // padded level rows (lookup_common.cuh)
 constexpr int kL2_WARP_FLOATS = kPyrWarpFloats;
 constexpr int kL2_OUT_PITCH = 144;                           // bytes per pixel of the e1 staging tile
-static_assert(32 * kA1Pitch * 2 <= 32 * kL2_P0 * 4, "the A tile aliases the level-0 rows");
-static_assert(32 * kL2_OUT_PITCH <= 32 * (kL2_P1 + kL2_P2) * 4, "the e1 staging tile aliases levels 1-2");
 
-template <int D>
-__global__ void __launch_bounds__(kL2_WARPS * 32, 3) lookup_enc1_v2_kernel(
-    const float* __restrict__ volume, const float* __restrict__ origin, float* __restrict__ disp,
-    const float* __restrict__ s9, int parts, const float* __restrict__ bd1, int apply_prev, float incre,
-    const __half* __restrict__ w1, const float* __restrict__ b1, __half* __restrict__ e1, int h, int w) {
-  static_assert(D % 4 == 0 && D <= 64 && D >= 8, "row registers / pitches are sized for D <= 64, 16-byte row pieces");
-  constexpr int NV = D / 4;                                  // 16-byte pieces per pixel row = row loads per lane
-  extern __shared__ __align__(16) unsigned char fsm[];
-  __half* sW = reinterpret_cast<__half*>(fsm);                                   // [48][kW1Pitch]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* L0 = reinterpret_cast<float*>(fsm + kCorrK * kW1Pitch * 2) + warp * kL2_WARP_FLOATS;
-  float* L1 = L0 + 32 * kL2_P0;
-  float* L2 = L1 + 32 * kL2_P1;
-  const int px = h * w;
-  // a warp past the end of the image (last CTA only) runs on pixel 0 with npix = 0: every store is guarded by npix, and
-  // the CTA keeps one barrier for all warps
-  const int p0_raw = (blockIdx.x * kL2_WARPS + warp) * 32;
-  const int p0 = p0_raw < px ? p0_raw : 0;
-  pdl_trigger();
-  // 1x1 weights: constants, requested before the dependency wait; they are parked in registers until the chunk's own
-  // loads are in flight too, so a CTA pays ONE global-latency exposure, not two (ncu: 20 % of the v2 kernel's stall
-  // samples sat on the weight store that used to come first)
-  constexpr int WQ = kCorrK * kHid / 8 / (kL2_WARPS * 32);
-  static_assert(WQ * kL2_WARPS * 32 * 8 == kCorrK * kHid, "weight pieces divide evenly over the CTA");
-  uint4 wreg[WQ];
-#pragma unroll
-  for (int q = 0; q < WQ; ++q) wreg[q] = __ldg(reinterpret_cast<const uint4*>(w1) + q * kL2_WARPS * 32 + tid);
-  pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
-  const int npix = p0_raw < px ? min(32, px - p0) : 0;
-  const bool live = lane < npix;
-  const int p = p0 + (live ? lane : 0);
-
-  // ---- issue every load of the chunk ----
-  float4 rv[NV];
-  pyr_load_chunk<D>(volume + (long long)p0 * D, npix, lane, rv);
-  float dsp = disp[p];
-  const float org = __ldg(origin + p);
-  float sv[9];
-  if (apply_prev) {     // K6 of the previous iteration: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t]))
-    const int x = p % w, y = p / w;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      sv[t] = 0.f;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-        const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
-        sv[t] = (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
-      }
-    }
-  }
-
-#pragma unroll
-  for (int q = 0; q < WQ; ++q) {
-    const int i = q * kL2_WARPS * 32 + tid;
-    *reinterpret_cast<uint4*>(sW + (i / (kHid / 8)) * kW1Pitch + (i % (kHid / 8)) * 8) = wreg[q];
-  }
-  // ---- pyramid rows -> shared memory ----
-  pyr_store_chunk<D>(rv, L0, L1, L2, lane);
-  if (apply_prev) {
-    float s = 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int x = p % w, y = p / w;
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += sv[t];
-    }
-    dsp += h_round(0.01f * h_round(s + __ldg(bd1)));
-    if (live) disp[p] = dsp;
-  }
-  const float c = live ? lookup_coord(dsp, org, incre, D) : 0.f;
-  __syncwarp();
-
-  // ---- 33 taps of this lane's pixel -> fp16 A row (registers) ----
-  uint32_t arow[kCorrK / 2];
-  {
-    float tp33[33], tp[kCorrK];
-    pyr_taps33<D>(L0, L1, L2, lane, c, tp33);
-#pragma unroll
-    for (int k = 0; k < kCorrPlanes; ++k) tp[k] = tp33[k];
-#pragma unroll
-    for (int k = kCorrPlanes; k < kCorrK; ++k) tp[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < kCorrK / 2; ++k) {
-      const __half2 hh = __floats2half2_rn(live ? tp[2 * k] : 0.f, live ? tp[2 * k + 1] : 0.f);
-      arow[k] = *reinterpret_cast<const uint32_t*>(&hh);
-    }
-  }
-  __syncwarp();                       // every lane is done with the pyramid rows: the A tile may overwrite level 0
-  __half* sA = reinterpret_cast<__half*>(L0);
-#pragma unroll
-  for (int k = 0; k < kCorrK / 8; ++k)
-    *reinterpret_cast<uint4*>(sA + lane * kA1Pitch + k * 8) =
-        make_uint4(arow[4 * k], arow[4 * k + 1], arow[4 * k + 2], arow[4 * k + 3]);
-  __syncthreads();                    // the only CTA barrier: the 1x1 weights of all four warps are in place (and my A tile)
-
-  // ---- 1x1 conv on mma.sync (two 16-pixel tiles), bias, fp16 rounding, ReLU -> staging tile ----
-  unsigned char* sO = reinterpret_cast<unsigned char*>(L1);
-  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * kW1Pitch + 8 * (lane >> 4)) * 2;
-  const int g = lane >> 2, q = lane & 3;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    float acc[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    const uint32_t aBase = smem_u32(sA) + ((mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kA1Pitch + 8 * (lane >> 4)) * 2;
-#pragma unroll
-    for (int k16 = 0; k16 < kCorrK / 16; ++k16) {
-      uint32_t a[4];
-      ldmatrix_x4(a, aBase + k16 * 32);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t b[4];
-        ldmatrix_x4_trans(b, bBase + (k16 * 16 * kW1Pitch + j * 16) * 2);
-        mma16816(acc[2 * j], a, b[0], b[1]);
-        mma16816(acc[2 * j + 1], a, b[2], b[3]);
-      }
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int row = mt * 16 + g + 8 * half;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = j * 8 + q * 2;
-        const float v0 = fmaxf(h_round(acc[j][2 * half] + __ldg(b1 + n)), 0.f);
-        const float v1 = fmaxf(h_round(acc[j][2 * half + 1] + __ldg(b1 + n + 1)), 0.f);
-        *reinterpret_cast<__half2*>(sO + row * kL2_OUT_PITCH + n * 2) = __floats2half2_rn(v0, v1);
-      }
-    }
-  }
-  __syncwarp();
-  // ---- e1: 4 pixels (512 contiguous bytes) per warp store ----
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int row = it * 4 + (lane >> 3), cchunk = lane & 7;
-    if (row < npix)
-      *reinterpret_cast<uint4*>(e1 + (long long)(p0 + row) * 64 + cchunk * 8) =
-          *reinterpret_cast<const uint4*>(sO + row * kL2_OUT_PITCH + cchunk * 16);
-  }
-}
-
-// KA v3: v2 with the level-0 rows only in shared memory (9.3 KB per warp, levels 1-2 pooled on the fly from the zero
-// padded row) and a register cap of 102: 20 resident warps per SM instead of 12.  ncu on v2: 17 % of the warp slots
-// active, every warp a long dependent chain -- the kernel wants more warps, not fewer instructions.
 static_assert(32 * kA1Pitch * 2 + 32 * kL2_OUT_PITCH <= kPyr0WarpFloats * 4, "A tile + e1 staging tile alias the level-0 rows");
 template <int D>
 __global__ void __launch_bounds__(kL2_WARPS * 32, 5) lookup_enc1_v3_kernel(
@@ -563,7 +416,6 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 5) lookup_enc1_v3_kernel(
 
 static size_t lookup_enc1_v3_smem() { return (size_t)kCorrK * kW1Pitch * 2 + (size_t)kL2_WARPS * kPyr0WarpFloats * 4; }
 
-static size_t lookup_enc1_v2_smem() { return (size_t)kCorrK * kW1Pitch * 2 + (size_t)kL2_WARPS * kL2_WARP_FLOATS * 4; }
 
 // ------------------------------------------------------------------------------------------
 // 3x3 implicit-GEMM convolution
@@ -579,7 +431,7 @@ template <int N_TILE>
 struct ConvSmem {
   static constexpr int B_PITCH = N_TILE + 8;             // halfs
   static constexpr int B_BYTES = 64 * B_PITCH * 2;
-  static constexpr int TOTAL = 2 * A_BYTES + NSTAGE * B_BYTES + (N_TILE == 256 ? (9 * 256 + 128 * 9) * 4 : 0);
+  static constexpr int TOTAL = 2 * A_BYTES + NSTAGE * B_BYTES + (N_TILE == 256 ? (9 * 256 + 4 * 128 * 9) * 4 : 0);
 };
 
 template <int N_TILE, int EPI>
@@ -678,10 +530,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) 
   if (EPI == EPI_DELTA) {
     // d = relu(fp16(acc + b)); s9[p][t] = sum_n w2[t][n] * d[n]  (second delta conv as 9 per-pixel dots)
     float* sW2 = reinterpret_cast<float*>(smem + 2 * A_BYTES + NSTAGE * S::B_BYTES);
-    float* sS9 = sW2 + 9 * 256;
+    float* sS9 = sW2 + 9 * 256;          // [column quarter wn][pixel 128][tap 9]: summed in a fixed order below
     __syncthreads();
     for (int i = tid; i < 9 * 256; i += 256) sW2[i] = __ldg(a.w2 + i);
-    for (int i = tid; i < 128 * 9; i += 256) sS9[i] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
@@ -710,10 +561,12 @@ __global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) 
       }
       if (q == 0) {
         const int pl = (wm * 4 + mi) * TW + g;
+        // every (pixel, tap) of a column quarter is written by exactly one lane: no atomics, so the sum over the four
+        // quarters below has a fixed order (shared-memory float atomics made the result depend on warp timing)
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          atomicAdd(sS9 + pl * 9 + t, t0[t]);
-          atomicAdd(sS9 + (pl + 8) * 9 + t, t1[t]);
+          sS9[(wn * 128 + pl) * 9 + t] = t0[t];
+          sS9[(wn * 128 + pl + 8) * 9 + t] = t1[t];
         }
       }
     }
@@ -721,7 +574,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) 
     for (int i = tid; i < 128 * 9; i += 256) {
       const int pl = i / 9, t = i % 9;
       const int yy = y0 + pl / TW, xx = x0 + pl % TW;
-      if (yy < a.h && xx < a.w) a.s9[((long long)yy * a.w + xx) * 18 + t] = sS9[i];
+      if (yy < a.h && xx < a.w)
+        a.s9[((long long)yy * a.w + xx) * 18 + t] = ((sS9[i] + sS9[128 * 9 + i]) + sS9[2 * 128 * 9 + i]) + sS9[3 * 128 * 9 + i];
     }
     return;
   }
@@ -806,15 +660,11 @@ static int configure_conv() {
   return CER_OK;
 }
 
-void tc_set_a_tma(int on);
-void tc_set_pair_mode(int gates_mode, int delta_mode);   // 0 single CTA, 1 cta_group::2 pairs, 2 multicast pairs, 3 two tiles, 4 3-tap stages
 static int g_variant = -1;
 int conv_variant() {
   if (g_variant < 0) {
     const char* e = getenv("CER_CONV");
     g_variant = (e && !strcmp(e, "hmma")) ? 0 : 1;
-    if (e && !strcmp(e, "tc2")) tc_set_pair_mode(1, 1);
-    if (e && !strcmp(e, "tc1")) tc_set_pair_mode(0, 0);
   }
   return g_variant;
 }
@@ -824,7 +674,7 @@ static int g_lookup_variant = -1;
 int lookup_variant() {
   if (g_lookup_variant < 0) {
     const char* e = getenv("CER_LOOKUP");
-    g_lookup_variant = (e && !strcmp(e, "v1")) ? 1 : (e && !strcmp(e, "v2")) ? 2 : 3;
+    g_lookup_variant = (e && !strcmp(e, "general")) ? 1 : 2;
   }
   return g_lookup_variant;
 }
@@ -842,10 +692,6 @@ int update_configure() {
   if ((rc = configure_conv<256, EPI_DELTA>())) return rc;
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)lookup_enc1_smem(256)));
-  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)lookup_enc1_v2_smem()));
-  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v2_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)lookup_enc1_v2_smem()));
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)lookup_enc1_v3_smem()));
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -912,18 +758,10 @@ int update_step_hmma(const void* blob, void* workspace, void* net, const void* i
 
 // One GRU iteration of the plan (core/raft.py:96-101): KA (apply pending delta, lookup, 1x1) + K2..K5.
 // The delta of THIS iteration stays pending in ws.s9 (applied by the next KA or by update_apply_delta).
-// Tile-level dependencies between the tcgen05 convs of an iteration (ConvArgs::flags_in / flags_out): 0 = every kernel
-// waits for its whole predecessor (default), 1 = per-tile flags (CER_TILE_FLAGS=1 / cer_set_tile_flags).  Measured on
-// B200 at cfg 2: 100.8 depth-maps/s with flags against 101.3 without -- the CTAs of the next conv cannot become resident
-// before the predecessor's CTA on that SM exits anyway (shared memory), and PDL already overlaps their prologue with it.
-static int g_tile_flags = -1;
-static int tile_flags() {
-  if (g_tile_flags < 0) {
-    const char* e = getenv("CER_TILE_FLAGS");
-    g_tile_flags = (e && !strcmp(e, "1")) ? 1 : 0;
-  }
-  return g_tile_flags;
-}
+// Tile-level dependencies between the tcgen05 convs of an iteration (ConvArgs::flags_in / flags_out) were measured in
+// round 1 (100.8 depth-maps/s with flags against 101.3 without) and are switched off: every kernel waits for its whole
+// predecessor through programmatic dependent launch.
+static int tile_flags() { return 0; }
 
 // Zero the tile flags of the next `iters` iterations (start of a stage; a memset node when captured).
 int update_reset_flags(void* workspace, int iters, int h, int w, cudaStream_t stream) {
@@ -953,7 +791,7 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
   const int n_flag_tiles = flag_tiles(h, w);
   auto F = [&](int k) { return flags_on ? ws.flags + ((size_t)iter * kFlagKernels + k) * n_flag_tiles : (int*)nullptr; };
   // the two cascade widths of the reference (core/raft.py:77-81) take the warp-autonomous kernel; any other D the general one
-  if (lookup_variant() == 3 && (D == 64 || D == 44)) {
+  if (lookup_variant() == 2 && (D == 64 || D == 44)) {
     const int grid = ceil_div(px, kL2_WARPS * 32);
     if (D == 64)
       CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v3_kernel<64>, grid, kL2_WARPS * 32, lookup_enc1_v3_smem(), stream, volume, origin,
@@ -961,16 +799,6 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
                      (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
     else
       CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v3_kernel<44>, grid, kL2_WARPS * 32, lookup_enc1_v3_smem(), stream, volume, origin,
-                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
-                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
-  } else if (lookup_variant() == 2 && (D == 64 || D == 44)) {
-    const int grid = ceil_div(px, kL2_WARPS * 32);
-    if (D == 64)
-      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v2_kernel<64>, grid, kL2_WARPS * 32, lookup_enc1_v2_smem(), stream, volume, origin,
-                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
-                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
-    else
-      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v2_kernel<44>, grid, kL2_WARPS * 32, lookup_enc1_v2_smem(), stream, volume, origin,
                      disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
                      (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
   } else {
@@ -1126,30 +954,15 @@ int cer_debug_set_conv_profile(void* dev_buf) {
 }
 
 int cer_set_conv_variant(int variant) {
-  CER_REQUIRE(variant >= 0 && variant <= 7,
-              "cer_set_conv_variant: 0 mma.sync, 1 tcgen05 cta_group::2 pairs for both wide convs, 2 tcgen05 one tile per CTA, "
-              "3 tcgen05 multicast pairs, 4 tcgen05 two tiles per CTA, 5 tcgen05 one tile per CTA with 3-tap weight stages, "
-              "6 cta_group::2 pairs for the gate conv + one tile per CTA for the delta conv (default), "
-              "7 pairs for the gate conv + two tiles per CTA for the delta conv");
-  g_variant = variant == 0 ? 0 : 1;
-  const int m = variant == 1 ? 1 : variant == 3 ? 2 : variant == 4 ? 3 : variant == 5 ? 4 : 0;
-  tc_set_pair_mode(variant >= 6 ? 1 : m, variant == 7 ? 3 : (variant == 5 || variant == 6) ? 0 : m);
-  return CER_OK;
-}
-
-int cer_set_conv_a_tma(int on) {
-  tc_set_a_tma(on);
-  return CER_OK;
-}
-
-int cer_set_tile_flags(int on) {
-  g_tile_flags = on ? 1 : 0;
+  CER_REQUIRE(variant == 0 || variant == 1,
+              "cer_set_conv_variant: 1 tcgen05.mma + TMEM (default), 0 mma.sync (the A/B twin every GPU test also runs on)");
+  g_variant = variant;
   return CER_OK;
 }
 
 int cer_set_lookup_variant(int variant) {
-  CER_REQUIRE(variant >= 1 && variant <= 3,
-              "cer_set_lookup_variant: 1 block-staged kernel, 2 warp-autonomous kernel, 3 warp-autonomous, level-0 rows only (default)");
+  CER_REQUIRE(variant == 1 || variant == 2,
+              "cer_set_lookup_variant: 2 warp-autonomous kernels for the reference configuration (default), 1 general kernels");
   set_lookup_variant(variant);
   return CER_OK;
 }

@@ -901,25 +901,13 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 // Mode of the streamed-weight convs (A/B switch), per kernel: [0] gate conv (N = 192), [1] delta conv (N = 256).
 // Measured default: CTA pairs for the gate conv (79 vs 84 us); the delta conv as single CTAs (43 us; as a pair with
 // resident half weight sets its M256 x N256 MMAs run at ~200 instead of 128 cycles: 48 us).
-static int g_pair_modes[2] = {TC_CG2, TC_SINGLE};
-
 template <int N, int EPI>
 static int tc_configure_one() {
   CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, TC_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 TcCfg<N, TC_SINGLE>::TOTAL));
-  if (N != 64) {
-    constexpr int M1 = N != 64 ? TC_CG2 : TC_SINGLE, M2 = N != 64 ? TC_MC2 : TC_SINGLE;
-    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<N, M1>::TOTAL));
-    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<N, M2>::TOTAL));
-    constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
-    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<N, M3>::TOTAL));
-    constexpr int M4 = N == 192 ? TC_S3 : TC_SINGLE;
-    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, M4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<N, M4>::TOTAL));
-  }
+  if (N == 192)
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, (N == 192 ? TC_CG2 : TC_SINGLE)>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<N, (N == 192 ? TC_CG2 : TC_SINGLE)>::TOTAL));
   return CER_OK;
 }
 
@@ -933,11 +921,6 @@ int tc_configure() {
 }
 
 int tc_num_tiles(int h, int w) { return ((w + TC_TW - 1) / TC_TW) * ((h + TC_TH - 1) / TC_TH); }
-
-void tc_set_pair_mode(int gates_mode, int delta_mode) {
-  g_pair_modes[0] = gates_mode;
-  g_pair_modes[1] = delta_mode;
-}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -970,16 +953,8 @@ static int make_weight_map(const void* base, size_t total_bytes, int half_bytes,
   return CER_OK;
 }
 
-// A operand by TMA tensor loads (default) or by 16-byte cp.async from three producer warps (CER_CONV_A=cpasync)
-static int g_a_tma = -1;
-static int a_tma() {
-  if (g_a_tma < 0) {
-    const char* e = getenv("CER_CONV_A");
-    g_a_tma = (e && !strcmp(e, "cpasync")) ? 0 : 1;
-  }
-  return g_a_tma;
-}
-void tc_set_a_tma(int on) { g_a_tma = on ? 1 : 0; }
+// A operand by TMA tensor loads (the cp.async path of round 1 remains in the kernel as dead `use_tma == 0` code)
+static int a_tma() { return 1; }
 
 static int get_encode_fn(EncodeTiledFn* out) {
   static EncodeTiledFn fn = nullptr;
@@ -1071,34 +1046,13 @@ template <int N, int EPI>
 int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   const int tiles = ((a.w + TC_TW - 1) / TC_TW) * ((a.h + TC_TH - 1) / TC_TH);
   constexpr int kind = EPI == EPI_RELU ? KK_CONV_E : EPI == EPI_GATES ? KK_CONV_GATES : EPI == EPI_GRUOUT ? KK_CONV_Q : KK_CONV_DELTA;
-  const int g_pair_mode = N == 192 ? g_pair_modes[0] : N == 256 ? g_pair_modes[1] : TC_SINGLE;
   TcMaps amaps;
   {
     int rc = make_act_maps(a, &amaps);
     if (rc) return rc;
   }
-  if (N != 64 && tiles >= 2 && g_pair_mode == TC_MT2) {
-    constexpr int M3 = N != 64 ? TC_MT2 : TC_SINGLE;
-    const int units = (tiles + 1) / 2;
-    const int grid = units < kNumSMs ? units : kNumSMs;
-    CUtensorMap nomap;
-    memset(&nomap, 0, sizeof(nomap));
-    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M3>), grid, tc_threads(EPI), (TcCfg<N, M3>::TOTAL), stream, a, nomap, amaps);
-    return check_launch("conv3x3_tc");
-  }
-  if (N == 192 && g_pair_mode == TC_S3) {
-    constexpr int M4 = N == 192 ? TC_S3 : TC_SINGLE;
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    CUtensorMap nomap;
-    memset(&nomap, 0, sizeof(nomap));
-    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, M4>), grid, tc_threads(EPI), (TcCfg<N, M4>::TOTAL), stream, a, nomap, amaps);
-    return check_launch("conv3x3_tc");
-  }
-  if (N != 64 && tiles >= 2 && g_pair_mode != TC_SINGLE && g_pair_mode != TC_S3) {
-    constexpr int M1 = N != 64 ? TC_CG2 : TC_SINGLE, M2 = N != 64 ? TC_MC2 : TC_SINGLE;
-    return g_pair_mode == TC_CG2 ? launch_pair<N, EPI, M1>(a, tiles, kind, stream)
-                                 : launch_pair<N, EPI, M2>(a, tiles, kind, stream);
-  }
+  // the gate conv (N = 192) runs as cta_group::2 CTA pairs (79 vs 84 us); every other conv one 128-pixel tile per CTA
+  if (N == 192 && tiles >= 2) return launch_pair<N, EPI, (N == 192 ? TC_CG2 : TC_SINGLE)>(a, tiles, kind, stream);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
   CUtensorMap nomap;
   memset(&nomap, 0, sizeof(nomap));

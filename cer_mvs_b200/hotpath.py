@@ -8,8 +8,8 @@ on the device in the kernels' layouts.
     disp = hp(fmaps, net, inp, poses, intrinsics, scale)      # device tensors -> [1,1,h1,w1]
     disp = hp.run_host(fmaps_np, net_np, inp_np, poses_np, intrinsics_np, scale)   # host buffers
 
-Multi-GPU: ``forward_view_sharded`` lets every rank build the partial volume
-of its own source views, sums the partials with one all-reduce per stage, then iterates replicated.
+Multi-GPU: ``forward_sharded`` lets every rank build the partial volume of its own run of
+(view, hypothesis) units, sums the partials with one all-reduce per stage, then iterates replicated.
 """
 import ctypes as C
 
@@ -202,50 +202,43 @@ class DepthHotPath:
     def wait_host(self):
         _lib.check(_lib.lib().cer_plan_wait_host(self._plan), "cer_plan_wait_host")
 
-    def forward_view_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None, n_bands=1):
-        """One depth map over all ranks of ``group``: rank g builds views [g*V/G, (g+1)*V/G), the partial mean volume of
-        every stage is summed with ``n_bands`` all-reduces (one per band of image rows, each overlapping the build of
-        the next band), replicated GRU loop.  Measured on 2 x B200 (cfg 2): 8.05 ms per depth map with one all-reduce
-        per stage, 8.29 ms with four bands -- a 30 MB all-reduce over NVLink costs less than the extra launches, so one
-        band is the default; banding is for slower links / more ranks."""
+    def forward_sharded(self, fmaps, net, inp, poses, intrinsics, scale=1.0, group=None, out=None):
+        """One depth map over all ranks of ``group``.  The cost-volume build of a stage is
+        n_views * D independent (view, hypothesis) units (core/corr.py:84-91 sums independent per-view, per-hypothesis
+        terms); rank g builds the contiguous run ``unit_range(n_views * D, g, G)`` into a zeroed partial volume, ONE
+        all-reduce(sum) per stage adds the partial volumes, the GRU loop then runs replicated.  Any number of ranks
+        works, also more ranks than source views (BASELINE configs[4]: 7 views on 8 GPUs).  Every rank passes the
+        same inputs; only the views a rank touches are converted to the kernels' layout."""
         import torch.distributed as dist
-        from .dist import view_range
+        from .dist import unit_range, views_of_units
         n_views = self._check_maps(fmaps, net, inp, poses, intrinsics, out)
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        vb, ve = view_range(n_views, rank, world)
+        units = [unit_range(n_views * D, rank, world) for (D, _, _) in self.stages]
+        touched = [views_of_units(ub, ue, D) for (ub, ue), (D, _, _) in zip(units, self.stages)]
+        vb = min((t[0] for t in touched if t[1] > t[0]), default=0)
+        ve = max((t[1] for t in touched if t[1] > t[0]), default=0)
         L = _lib.lib()
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr()
             P, K = self._prep_cameras(poses, intrinsics, scale)
             fmaps, net, inp = fmaps.contiguous(), net.contiguous(), inp.contiguous()
             out = self._out if out is None else out
-            if ve > vb:
-                _lib.check(L.cer_plan_prepare(self._plan, fmaps.data_ptr(), int(fmaps.dtype == torch.float16),
-                                              net.data_ptr(), inp.data_ptr(), int(net.dtype == torch.float16),
-                                              P.data_ptr(), K.data_ptr(), n_views, vb, ve, st), "cer_plan_prepare")
-            else:
-                raise RuntimeError("more ranks than source views: use replica mode for the surplus ranks")
+            _lib.check(L.cer_plan_prepare(self._plan, fmaps.data_ptr(), int(fmaps.dtype == torch.float16),
+                                          net.data_ptr(), inp.data_ptr(), int(net.dtype == torch.float16),
+                                          P.data_ptr(), K.data_ptr(), n_views, vb, ve, st), "cer_plan_prepare")
             for s in range(len(self.stages)):
                 n = C.c_size_t()
                 ptr = L.cer_plan_partial_volume(self._plan, s, C.byref(n))
                 vol = torch.as_tensor(_DevView(ptr, n.value), device=self.device)
-                D = self.stages[s][0]
-                # band i's all-reduce (NCCL's own stream) overlaps the build of band i+1 (SURVEY.md 8e); bands are
-                # whole 8-row tile rows, the volume is row-major so a band is one contiguous slice
-                rows = -(-self.h1 // max(int(n_bands), 1))
-                rows = max(8, -(-rows // 8) * 8)
-                works = []
-                for y0 in range(0, self.h1, rows):
-                    y1 = min(y0 + rows, self.h1)
-                    _lib.check(L.cer_plan_build_stage_rows(self._plan, s, y0, y1, st), "cer_plan_build_stage_rows")
-                    works.append(dist.all_reduce(vol[y0 * self.w1 * D:y1 * self.w1 * D], op=dist.ReduceOp.SUM,
-                                                 group=group, async_op=True))
-                for wk in works:
-                    wk.wait()
+                ub, ue = units[s]
+                _lib.check(L.cer_plan_build_stage_units(self._plan, s, ub, ue, st), "cer_plan_build_stage_units")
+                dist.all_reduce(vol, op=dist.ReduceOp.SUM, group=group)
                 _lib.check(L.cer_plan_iterate_stage(self._plan, s, st), "cer_plan_iterate_stage")
             _lib.check(L.cer_plan_finish(self._plan, 1.0 if scale is None else float(scale), out.data_ptr(), st),
                        "cer_plan_finish")
         return out
+
+    forward_view_sharded = forward_sharded      # round-1 name
 
     KERNEL_KINDS = ["layout", "projection", "volume_build", "pool", "lookup", "corr_dropin", "disp_encoder",
                     "corr_enc_1x1", "conv_corr_enc_3x3", "conv_gates", "conv_q_gru", "conv_delta", "disp_update",

@@ -76,14 +76,16 @@ int cer_build_volume(const void* feats, int feats_f16, const float* Pij, const i
                      float* origin, float* volume, float out_scale, int per_view, int h, int w,
                      cer_stream_t stream);
 
-/* The same for image rows [y_begin, y_end) only (y_begin a multiple of 8; fp16 features, default kernel): a caller that
- * shards source views over GPUs all-reduces one band of the partial volume while the next band is built. */
-int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
+/* Hypotheses [d_begin, d_end) of the given views only (fp16 features); accumulate != 0 ADDS the result to `volume`
+ * instead of overwriting it.  This is the unit of work of the sharded build: a rank owns a contiguous run of
+ * (view, hypothesis) units, builds it into a zeroed partial volume, and the partial volumes are summed by one
+ * all-reduce (core/corr.py:84-91 is a sum over views of independent per-hypothesis terms). */
+int cer_build_volume_part(const void* feats, int feats_f16, const float* Pij, const int* ii, const int* jj,
                           int n_pairs, const float* disp_in, int shift, int D, float incre, float lo_origin,
-                          float* origin, float* volume, float out_scale, int per_view, int h, int w, int y_begin,
-                          int y_end, cer_stream_t stream);
+                          float* origin, float* volume, float out_scale, int per_view, int h, int w, int d_begin,
+                          int d_end, int accumulate, cer_stream_t stream);
 
-/* Kernel used for fp16 features (cer_build_volume / cer_build_volume_rows and the plan):
+/* Kernel used for fp16 features (cer_build_volume / cer_build_volume_part and the plan):
  *   0 = shared-memory-staged source boxes: TMA tensor loads of the epipolar bounding box of a 16 x 8 pixel tile and a
  *       chunk of hypotheses, tile-vs-box dots on tcgen05.mma, bilinear blend of correlation scalars (default;
  *       csrc/build_volume_tc.cu);
@@ -91,6 +93,9 @@ int cer_build_volume_rows(const void* feats, int feats_f16, const float* Pij, co
  * Both restate core/corr.py:46-97 + alt_cuda_corr.forward (radius 0); they differ in the summation order of the
  * 64-channel dot only.  fp32 features always use the generic gather kernel with plain FFMA. */
 int cer_set_build_variant(int variant);
+/* Debug / profiling: 16 x uint64 device counters filled by the staged build kernel (chunks, plan attempts, MMA / ZERO /
+ * DIRECT chunks, sum of chunk lengths, sum of MMA N, cycles per role; layout in csrc/build_volume_tc.cu); NULL = off. */
+int cer_debug_set_build_profile(unsigned long long* dev_counters);
 
 /* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
 int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stream_t stream);
@@ -133,37 +138,20 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
                     const float* corr, int slots, float* delta, int apply_delta, int stage, int h, int w,
                     cer_stream_t stream);
 
-/* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on all of them):
- *   6 = default (CER_CONV unset): tcgen05.mma + TMEM, persistent CTAs; the gate conv (N = 192) as CTA pairs issuing
- *       cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), every other conv one 128-pixel tile per CTA
- *   1 = both wide convs as cta_group::2 pairs, the delta conv with its half weight set resident (CER_CONV=tc2)
- *   7 = pairs for the gate conv, two tiles per CTA for the delta conv
- *   2 = every conv one 128-pixel tile per CTA at a time (CER_CONV=tc1)
- *   3 = the N >= 192 convolutions as 2-CTA clusters that multicast each weight tile
- *   4 = the N >= 192 convolutions with two 128-pixel tiles per CTA sharing each weight stage
- *   5 = the gate conv with a whole kernel row (3 taps) per weight stage, one tile per CTA
- *   0 = mma.sync (the v1 kernels; CER_CONV=hmma).
- * Takes effect for launches and graph captures issued afterwards. */
+/* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on both):
+ *   1 = default (CER_CONV unset): tcgen05.mma + TMEM, persistent CTAs, TMA operand loads; the gate conv (N = 192) as CTA
+ *       pairs issuing cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), every other conv one
+ *       128-pixel tile per CTA (csrc/update_tc.cu)
+ *   0 = mma.sync (the v1 kernels, csrc/update_hmma.cu; CER_CONV=hmma).
+ * Takes effect for launches and graph captures issued afterwards (a plan that has already captured its graphs keeps
+ * the variant it captured). */
 int cer_set_conv_variant(int variant);
 
 /* Which lookup kernels are used (A/B switch; results are bit-identical):
- *   3 = default: warp-autonomous kernels for the reference configuration (radius 5, 3 levels, D = 64 / 44); the plan's
- *       fused lookup + 1x1-encoder kernel keeps only the level-0 rows in shared memory (20 warps per SM)
- *   2 = the fused kernel with all three pyramid levels materialised in shared memory (12 warps per SM; CER_LOOKUP=v2)
- *   1 = the general block-staged kernels only (any D <= 256 / any radius; CER_LOOKUP=v1). */
+ *   2 = default: warp-autonomous kernels for the reference configuration (radius 5, 3 levels, D = 64 / 44); the plan's
+ *       fused lookup + 1x1-encoder kernel keeps only the level-0 rows in shared memory
+ *   1 = the general block-staged kernels only (any D <= 1024 / any radius; CER_LOOKUP=general). */
 int cer_set_lookup_variant(int variant);
-
-/* How the tcgen05 convolutions bring in their activation (A) operand: 1 = one TMA tensor load per 64-channel halo chunk
- * (4-D view of the NHWC tensor, zero fill outside the image = the conv padding; default), 0 = 16-byte cp.async from the
- * producer warps (CER_CONV_A=cpasync).  Bit-identical results. */
-int cer_set_conv_a_tma(int on);
-
-/* Tile-level dependencies between the tensor-core convolutions of a plan iteration (opt-in, default off: measured no
- * faster than grid-level programmatic dependent launch on B200; CER_TILE_FLAGS=1):
- * a conv publishes one flag per finished 16 x 8 tile and the next conv waits for the 3 x 3 tile neighbourhood it reads
- * instead of for the whole grid, so its CTAs start on the SMs the predecessor's last round leaves idle.  Results are
- * bit-identical either way. */
-int cer_set_tile_flags(int on);
 
 /* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */
 int cer_debug_set_conv_profile(void* dev_buf);
@@ -254,15 +242,17 @@ int cer_plan_submit_host(cer_plan* plan, const void* fmaps, int fmaps_f16, const
                          float* disp_out_host, cer_stream_t stream);
 int cer_plan_wait_host(cer_plan* plan);
 
-/* Stage-wise API for view-sharded multi-GPU runs: prepare -> for each stage
- * { build_stage (local views, scaled 1/total_views) ; [caller all-reduces partial_volume] ;
- * iterate_stage } -> finish. */
+/* Stage-wise API for sharded multi-GPU runs: prepare (the views this rank touches; an empty
+ * range converts the reference image and the context only) -> for each stage { build_stage_units (this rank's run of
+ * (view, hypothesis) units, scaled 1/total_views) ; [caller all-reduces partial_volume] ; iterate_stage } -> finish. */
 int cer_plan_prepare(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
                      int ctx_f16, const float* poses, const float* intrinsics, int n_views,
                      int view_begin, int view_end, cer_stream_t stream);
 int cer_plan_build_stage(cer_plan* plan, int stage, cer_stream_t stream);
-/* Rows [y_begin, y_end) of the stage's partial volume (see cer_build_volume_rows). */
-int cer_plan_build_stage_rows(cer_plan* plan, int stage, int y_begin, int y_end, cer_stream_t stream);
+/* Sharded build: units [unit_begin, unit_end) of the stage's n_views * D (view, hypothesis) units, view-major, into a
+ * zeroed partial volume (cer_plan_partial_volume); the views they touch must have been prepared.  An empty range only
+ * zeroes the volume and writes the hypothesis origin (every rank runs the lookups). */
+int cer_plan_build_stage_units(cer_plan* plan, int stage, long long unit_begin, long long unit_end, cer_stream_t stream);
 float* cer_plan_partial_volume(cer_plan* plan, int stage, size_t* n_floats);
 int cer_plan_iterate_stage(cer_plan* plan, int stage, cer_stream_t stream);
 int cer_plan_finish(cer_plan* plan, float out_scale, float* disp_out, cer_stream_t stream);

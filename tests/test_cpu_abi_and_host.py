@@ -102,6 +102,65 @@ def test_stage_params_and_partitioning():
         view_range(4, 4, 4)
 
 
+def test_unit_sharding_covers_every_unit_once():
+    """(view, hypothesis) units of the sharded build, incl. more ranks than views (cfg 5: 7 views / 8 GPUs)."""
+    from cer_mvs_b200.dist import unit_range, views_of_units
+    for V, D, G in [(7, 64, 8), (7, 44, 8), (10, 64, 4), (15, 44, 4), (1, 64, 8), (3, 64, 2), (2, 4, 16)]:
+        seen = np.zeros(V * D, np.int32)
+        for r in range(G):
+            ub, ue = unit_range(V * D, r, G)
+            seen[ub:ue] += 1
+            vb, ve = views_of_units(ub, ue, D)
+            if ue > ub:
+                assert vb * D <= ub and ue <= ve * D and ve - vb <= (ue - ub + D - 1) // D + 1
+                # the three kernel calls of cer_plan_build_stage_units: tail of the first view, whole views, head of the last
+                a, b = ub % D, (ue - 1) % D + 1
+                calls = [(vb, vb + 1, a, b)] if ve - vb == 1 else (
+                    ([(vb, vb + 1, a, D)] if a else []) + ([(ve - 1, ve, 0, b)] if b < D else []) +
+                    [(vb + (1 if a else 0), ve - (1 if b < D else 0), 0, D)])
+                cover = np.zeros(V * D, np.int32)
+                for v0, v1, d0, d1 in calls:
+                    for v in range(v0, v1):
+                        cover[v * D + d0:v * D + d1] += 1
+                want = np.zeros(V * D, np.int32)
+                want[ub:ue] = 1
+                assert np.array_equal(cover, want)
+            else:
+                assert (vb, ve) == (0, 0)
+        assert (seen == 1).all()
+    assert [unit_range(7 * 64, r, 8) for r in range(8)][0] == (0, 56)          # SURVEY 8e: 448 units -> 56 per GPU
+
+
+def _gloo_worker(rank, world, port, ret):
+    """world_size-2 CPU stand-in for the sharded build: every rank sums its own units of a [V, px, D] table into a
+    partial volume, one all_reduce(sum) -- the host logic of DepthHotPath.forward_sharded without a GPU."""
+    import torch.distributed as dist
+    from cer_mvs_b200.dist import unit_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V, px, D = 3, 11, 8
+    g = torch.Generator().manual_seed(0)
+    per_view = torch.randn(V, px, D, generator=g)
+    ub, ue = unit_range(V * D, rank, world)
+    part = torch.zeros(px, D)
+    for u in range(ub, ue):
+        part[:, u % D] += per_view[u // D, :, u % D] / V
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ret["sum"] = part.numpy()
+        ret["want"] = per_view.mean(0).numpy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_build_host_logic_gloo_world2():
+    import torch.multiprocessing as mp
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gloo_worker, args=(2, 29611, ret), nprocs=2, join=True)
+        np.testing.assert_allclose(ret["sum"], ret["want"], rtol=1e-6, atol=1e-6)
+
+
 def test_update_block_state_dict_matches_reference_keys():
     from cer_mvs_b200.update import ConvGRU, UpdateBlock
     ub = UpdateBlock(cascade=[(64, 64, 8), (-1, 320, 8)], dim_net=64, dim_inp=64)

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 STAGES = [(64, 0.0025 / 64, True), (44, 0.0025 / 320, False)]
 
 
-def _build(variant, fm, poses, K, disp_in, stage, per_view=False, rows=None):
+def _build(variant, fm, poses, K, disp_in, stage, per_view=False, parts=None):
     """cer_build_volume(_rows) on NHWC fp16 features prepared by cer_nchw_to_nhwc; returns (volume, origin)."""
     L = _lib.lib()
     st = _lib.stream_ptr()
@@ -34,10 +34,17 @@ def _build(variant, fm, poses, K, disp_in, stage, per_view=False, rows=None):
     lo = float(torch.tensor(D // 2 * incre).float())
     _lib.check(L.cer_set_build_variant(variant))
     try:
-        y0, y1 = rows if rows else (0, h)
-        _lib.check(L.cer_build_volume_rows(feats.data_ptr(), 1, Pij.data_ptr(), ii.data_ptr(), jj.data_ptr(), V,
-                                           disp_in.data_ptr(), int(shift), D, incre, lo, origin.data_ptr(),
-                                           vol.data_ptr(), 1.0 if per_view else 1.0 / V, int(per_view), h, w, y0, y1, st))
+        if parts is None:
+            _lib.check(L.cer_build_volume(feats.data_ptr(), 1, Pij.data_ptr(), ii.data_ptr(), jj.data_ptr(), V,
+                                          disp_in.data_ptr(), int(shift), D, incre, lo, origin.data_ptr(),
+                                          vol.data_ptr(), 1.0 if per_view else 1.0 / V, int(per_view), h, w, st))
+        else:
+            # parts: [(view_begin, view_end, d_begin, d_end)] accumulated into a zeroed volume (the sharded build)
+            vol.zero_()
+            for vb, ve, d0, d1 in parts:
+                _lib.check(L.cer_build_volume_part(feats.data_ptr(), 1, Pij[vb:].data_ptr(), ii[vb:].data_ptr(),
+                                                   jj[vb:].data_ptr(), ve - vb, disp_in.data_ptr(), int(shift), D, incre,
+                                                   lo, origin.data_ptr(), vol.data_ptr(), 1.0 / V, 0, h, w, d0, d1, 1, st))
         torch.cuda.synchronize()
     finally:
         L.cer_set_build_variant(0)
@@ -115,16 +122,37 @@ def test_degenerate_geometry(case, stage):
           f"nonzero fraction {float((want != 0).float().mean()):.3f}")
 
 
-def test_row_bands_equal_whole():
-    fm, poses, K, disp = _scene(160, 112, 3, seed=46, stage=1)
-    whole, _ = _build(0, fm, poses, K, disp, 1)
-    L = _lib.lib()
-    h, w = 40, 28
-    parts = []
-    for y0, y1 in ((0, 16), (16, 24), (24, 40)):
-        v, _ = _build(0, fm, poses, K, disp, 1, rows=(y0, y1))
-        parts.append(v[0, y0 * w:y1 * w])
-    assert torch.equal(torch.cat(parts, 0), whole[0])
+@pytest.mark.parametrize("noise_steps", [0.5, 3.0, 30.0, 300.0])
+def test_noisy_disparity_input(noise_steps):
+    """Second cascade stage on a disparity map that is noisy from pixel to pixel (what an untrained GRU produces): the
+    samples of neighbouring pixels are far apart, tiles whose hypothesis origins differ by more than a few steps are
+    flagged by the staged kernel and computed by the gather kernel -- the result is the same either way."""
+    fm, poses, K, disp = _scene(160, 224, 3, seed=48, stage=1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    incre = STAGES[1][1]
+    noisy = disp + (torch.rand(disp.shape, device="cuda", generator=g) - 0.5) * 2 * noise_steps * incre
+    noisy[:8, :] = disp[:8, :]                     # a coherent band stays on the staged path
+    got, _ = _build(0, fm, poses, K, noisy.contiguous(), 1)
+    want, _ = _build(1, fm, poses, K, noisy.contiguous(), 1)
+    err = _compare(got, want)
+    frac_equal = float((got == want).float().mean())
+    print(f"noise {noise_steps} steps: max |staged - gather| = {err:.2e}, bit-equal fraction {frac_equal:.3f}")
+    if noise_steps >= 30:
+        assert frac_equal > 0.8                    # most tiles were handed to the gather kernel
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("stage", [0, 1])
+def test_unit_parts_add_up_to_whole(variant, stage):
+    """(view, hypothesis) parts accumulated into a zeroed volume == the whole build (up to the order of the view sum)."""
+    fm, poses, K, disp = _scene(160, 112, 3, seed=46, stage=stage)
+    D = STAGES[stage][0]
+    whole, _ = _build(variant, fm, poses, K, disp, stage)
+    parts = [(0, 1, 0, D), (1, 2, 0, 17), (1, 2, 17, D), (2, 3, 0, 5), (2, 3, 5, 6), (2, 3, 6, D)]
+    got, _ = _build(variant, fm, poses, K, disp, stage, parts=parts)
+    _compare(got, whole, tol=1e-6)
+    two, _ = _build(variant, fm, poses, K, disp, stage, parts=[(0, 2, 0, D), (2, 3, 0, D)])
+    _compare(two, whole, tol=1e-6)
 
 
 @pytest.mark.parametrize("cfg", ["cfg2_dtu_1184x1600_v10", "cfg5_blended_1536x2048_v7"])

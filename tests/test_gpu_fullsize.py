@@ -125,74 +125,3 @@ def test_hot_path_full_size_deterministic_and_graph_equals_eager():
         assert torch.isfinite(a).all()
         outs.append(a)
     assert torch.equal(outs[0], outs[1])
-
-
-@pytest.mark.parametrize("cfg", ["cfg2", "ragged"])
-def test_tile_flag_dependencies_do_not_change_results(cfg):
-    """Tile-level dependencies between the convs of an iteration (cer_set_tile_flags) only change WHEN a tile may
-    start: 3+3 iterations at a full-size grid (7 tile rounds per SM) and at a ragged one (partial edge tiles, fewer
-    tiles than SMs in the last round) give the same bits with and without them, graph and eager, every conv variant
-    that publishes / consumes flags."""
-    from cer_mvs_b200 import _lib
-    from cer_mvs_b200.hotpath import DepthHotPath
-    h1, w1, V = GRIDS["cfg2"] if cfg == "cfg2" else (203, 157, 3)
-    V = min(V, 3)
-    poses, K = synth.make_cameras(V, 4 * h1, 4 * w1, seed=0)
-    g = torch.Generator(device="cuda").manual_seed(5)
-    fm = torch.randn(1, V + 1, 64, h1, w1, generator=g, device="cuda").half()
-    net = torch.tanh(torch.randn(1, 1, 64, h1, w1, generator=g, device="cuda")).half()
-    inp = torch.relu(torch.randn(1, 1, 64, h1, w1, generator=g, device="cuda")).half()
-    sd = synth.make_update_weights(seed=0, delta_scale=0.1, delta_bias=0.005)
-    P, Kt = torch.from_numpy(poses)[None].cuda(), torch.from_numpy(K)[None].cuda()
-    outs = {}
-    try:
-        for variant in (6, 1, 2):
-            _lib.check(_lib.lib().cer_set_conv_variant(variant))
-            for flags in (0, 1):
-                _lib.check(_lib.lib().cer_set_tile_flags(flags))
-                for use_graph in (True, False):
-                    hp = DepthHotPath(h1, w1, max_views=V, cascade=[(64, 64, 3), (-1, 320, 3)], use_graph=use_graph)
-                    hp.load_update_block(sd)
-                    for rep in range(2):                      # the second run re-uses (and must re-zero) the flags
-                        outs[(variant, flags, use_graph, rep)] = hp(fm, net, inp, P, Kt, 1.0).clone()
-    finally:
-        _lib.lib().cer_set_tile_flags(0)
-        _lib.lib().cer_set_conv_variant(6)
-    for variant in (6, 1, 2):
-        ref = outs[(variant, 0, False, 0)]
-        assert torch.isfinite(ref).all()
-        for k, o in outs.items():
-            if k[0] == variant:
-                assert torch.equal(o, ref), k
-
-
-@pytest.mark.parametrize("grid", [(203, 157), (37, 53), (296, 400)])
-def test_conv_a_operand_tma_equals_cpasync(grid):
-    """The activation halo tiles arrive either by one 4-D TMA tensor load per chunk (zero fill outside the image) or by
-    16-byte cp.async with explicit zero fill: same bits, on ragged grids (partial edge tiles) and at the full size."""
-    from cer_mvs_b200 import _lib
-    from cer_mvs_b200.hotpath import DepthHotPath
-    h1, w1 = grid
-    V = 2
-    poses, K = synth.make_cameras(V, 4 * h1, 4 * w1, seed=0)
-    g = torch.Generator(device="cuda").manual_seed(7)
-    fm = torch.randn(1, V + 1, 64, h1, w1, generator=g, device="cuda").half()
-    net = torch.tanh(torch.randn(1, 1, 64, h1, w1, generator=g, device="cuda")).half()
-    inp = torch.relu(torch.randn(1, 1, 64, h1, w1, generator=g, device="cuda")).half()
-    sd = synth.make_update_weights(seed=0, delta_scale=0.1, delta_bias=0.005)
-    P, Kt = torch.from_numpy(poses)[None].cuda(), torch.from_numpy(K)[None].cuda()
-    outs = {}
-    try:
-        for variant in (6, 1, 2):
-            _lib.check(_lib.lib().cer_set_conv_variant(variant))
-            for tma in (0, 1):
-                _lib.check(_lib.lib().cer_set_conv_a_tma(tma))
-                hp = DepthHotPath(h1, w1, max_views=V, cascade=[(64, 64, 2), (-1, 320, 2)], use_graph=bool(tma))
-                hp.load_update_block(sd)
-                outs[(variant, tma)] = hp(fm, net, inp, P, Kt, 1.0).clone()
-    finally:
-        _lib.lib().cer_set_conv_a_tma(1)
-        _lib.lib().cer_set_conv_variant(6)
-    for variant in (6, 1, 2):
-        assert torch.isfinite(outs[(variant, 0)]).all()
-        assert torch.equal(outs[(variant, 0)], outs[(variant, 1)]), variant

@@ -11,13 +11,13 @@ from util import V, h1, rel_l1, t, w1
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["default", "tcgen05", "tcgen05_3tap", "tcgen05_two_tiles", "tcgen05_multicast", "tcgen05_pairs_both", "tcgen05_pair_two_tiles", "hmma"], autouse=True)
+@pytest.fixture(params=["default", "hmma"], autouse=True)
 def conv_variant(request):
     """Every test runs on both tensor-core paths: tcgen05.mma + TMEM (default) and mma.sync (v1)."""
     from cer_mvs_b200 import _lib
-    _lib.check(_lib.lib().cer_set_conv_variant({"default": 6, "tcgen05": 2, "tcgen05_3tap": 5, "tcgen05_two_tiles": 4, "tcgen05_multicast": 3, "tcgen05_pairs_both": 1, "tcgen05_pair_two_tiles": 7, "hmma": 0}[request.param]))
+    _lib.check(_lib.lib().cer_set_conv_variant({"default": 1, "hmma": 0}[request.param]))
     yield request.param
-    _lib.lib().cer_set_conv_variant(6)
+    _lib.lib().cer_set_conv_variant(1)
 
 
 def _ub(sd_np):
