@@ -43,6 +43,11 @@ SIGNATURES = {
     "cer_multires_merge": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "cer_geo_mats_bytes": (c_size_t, [c_int]),
     "cer_geometric_filter": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_double, c_double] + [c_void_p] * 10),
+    "cer_encoder_blob_bytes": (c_size_t, [c_int]),
+    "cer_encoder_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cer_pack_encoder_weights": (c_int, [c_void_p, c_int, c_void_p]),
+    "cer_encoder_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_float, c_void_p]),
     "cer_set_conv_variant": (c_int, [c_int]),
     "cer_set_lookup_variant": (c_int, [c_int]),
     "cer_debug_set_conv_profile": (c_int, [c_void_p]),

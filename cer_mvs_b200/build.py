@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libcer_mvs_b200.so")
-SOURCES = ["corr_ops.cu", "build_volume.cu", "build_volume_tc.cu", "update_hmma.cu", "update_tc.cu", "plan.cu", "io_ops.cu", "fusion_ops.cu"]
+SOURCES = ["corr_ops.cu", "build_volume.cu", "build_volume_tc.cu", "update_hmma.cu", "update_tc.cu", "plan.cu", "io_ops.cu", "fusion_ops.cu", "encoder.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -1,0 +1,609 @@
+// BasicEncoder (core/extractor.py:62-155, "HR" type: conv1 7x7/s2 -> layer1 (2 residual blocks @32) -> layer2
+// (2 residual blocks @64, stride 2) -> conv2 1x1), the producer of the hot path's inputs (core/raft.py:57,66-69):
+// fnet with instance norm, cnet without norm.  SURVEY.md section 8(f) row 1.
+//
+// Numerics = the reference under torch.cuda.amp.autocast: fp16 operands, fp32 accumulation, every conv output rounded to
+// fp16; instance-norm statistics in fp32 over the fp16-rounded conv output (biased variance, eps 1e-5), its output
+// rounded to fp16; residual sums in fp16.
+//
+// Layout: every activation is NHWC fp16 ([y][x][C]: a pixel's channels are one 64- or 128-byte row), so the implicit
+// GEMMs read their A operand with ldmatrix straight from a halo tile in shared memory; the last conv writes the feature
+// map in the cost-volume build's own layout (NHWC fp16, optionally pre-scaled by 1/8, core/corr.py:30-31) and / or in
+// the reference's NCHW layout.
+//
+// Kernels (all mma.sync m16n8k16, 256 threads, one 16 x 8 output tile per CTA, warp = one tile row x all channels):
+//   enc_conv1_kernel          7x7 stride 2, 3 -> 32, input normalisation (x*2/255 - 1, core/raft.py:40-41) fused
+//   enc_conv3x3_kernel        3x3, CIN/COUT in {32, 64}, stride 1 or 2
+//   enc_conv1x1_kernel        1x1 stride 2 (down-sample branch) and the final 1x1 (64 -> 64 | 128) with its epilogues
+//   enc_stats_kernel          per-channel mean / rstd from the per-CTA partial sums (fixed order: deterministic)
+//   enc_norm_kernel           relu(norm(a)) [+ b | + norm(b)] -> relu   (the block structure of ResidualBlock.forward)
+#include <stdlib.h>
+#include <string.h>
+
+#include "update_common.cuh"
+
+namespace cer {
+
+namespace {
+
+__device__ __forceinline__ void e_cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void e_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void e_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void e_ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void e_ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void e_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int ETW = 16, ETH = 8;      // output tile
+
+// Epilogue shared by the convs that feed a norm: acc (+bias) -> fp16 -> NHWC store, and the tile's per-channel sum / sum
+// of squares of the ROUNDED values -> stats_part[cta][COUT][2] (summed later in a fixed order).
+// Fragment layout of m16n8k16 accumulators: c[0], c[1] = row g, columns 2q, 2q+1; c[2], c[3] = row g + 8.
+template <int COUT>
+__device__ __forceinline__ void conv_epilogue(float (&acc)[COUT / 8][4], const float* __restrict__ bias,
+                                              __half* __restrict__ out, int ow, int oh, int x0, int y, int lane, int warp,
+                                              float* __restrict__ stats_part, float* sred /* [8][COUT][2] */) {
+  const int g = lane >> 2, q = lane & 3;
+  const bool row_ok = y < oh;
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j) {
+    const int n = j * 8 + q * 2;
+    const float b0 = __ldg(bias + n), b1 = __ldg(bias + n + 1);
+    float s0 = 0.f, s1 = 0.f, ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int x = x0 + g + 8 * half;
+      const __half2 hv = __floats2half2_rn(acc[j][2 * half] + b0, acc[j][2 * half + 1] + b1);
+      if (row_ok && x < ow) {
+        *reinterpret_cast<__half2*>(out + ((long long)y * ow + x) * COUT + n) = hv;
+        const float2 f = __half22float2(hv);
+        s0 += f.x; s1 += f.y; ss0 += f.x * f.x; ss1 += f.y * f.y;
+      }
+    }
+    if (stats_part != nullptr) {
+      // sum over the 8 row groups (lanes with the same q): xor 4, 8, 16
+#pragma unroll
+      for (int m = 4; m <= 16; m <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, m);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, m);
+      }
+      if (g == 0) {
+        float* d = sred + (warp * COUT + n) * 2;
+        d[0] = s0; d[1] = ss0; d[2] = s1; d[3] = ss1;
+      }
+    }
+  }
+  if (stats_part != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * 2; i += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) t += sred[wq * COUT * 2 + i];
+      stats_part[(long long)blockIdx.x * COUT * 2 + i] = t;
+    }
+  }
+}
+
+// ---- conv1: 7x7 stride 2 pad 3, 3 -> 32 ---------------------------------------------------------------------------
+// Input: one image, NCHW fp32 in 0..255 (normalised here).  The (2*16+5) x (2*8+5) x 3 input patch of a tile sits in
+// shared memory as fp16 [row][x][c]; for a kernel row ky the 21 values (kx, c) of an output pixel are contiguous there,
+// so K is walked as 7 x 32 (21 real + 11 columns whose weights are zero) and the A fragments are 4-byte loads.
+constexpr int C1_PW = 2 * ETW + 5, C1_PH = 2 * ETH + 5;      // 37 x 21
+constexpr int C1_PITCH = 128;                                // halfs per patch row (111 used + slack for the padded K)
+constexpr int C1_WPITCH = 32 + 8;
+__global__ void __launch_bounds__(256) enc_conv1_kernel(const float* __restrict__ img, int H, int W,
+                                                        const __half* __restrict__ wk /* [7][32][32] k-major */,
+                                                        const float* __restrict__ bias, __half* __restrict__ out, int oh,
+                                                        int ow, int normalize, float* __restrict__ stats_part) {
+  __shared__ __align__(16) __half sP[(C1_PH + 1) * C1_PITCH];
+  __shared__ __align__(16) __half sW[7 * 32 * C1_WPITCH];
+  __shared__ float sred[8 * 32 * 2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_x = (ow + ETW - 1) / ETW;
+  const int x0 = (blockIdx.x % tiles_x) * ETW, y0 = (blockIdx.x / tiles_x) * ETH;
+  for (int i = tid; i < 7 * 32 * 4; i += 256) {          // weights: 16-byte pieces
+    const int k = i >> 2, c = i & 3;
+    *reinterpret_cast<uint4*>(sW + k * C1_WPITCH + c * 8) = __ldg(reinterpret_cast<const uint4*>(wk) + i);
+  }
+  const long long plane = (long long)H * W;
+  for (int i = tid; i < (C1_PH + 1) * C1_PITCH; i += 256) {
+    const int r = i / C1_PITCH, e = i % C1_PITCH;
+    float v = 0.f;
+    if (r < C1_PH && e < C1_PW * 3) {
+      const int px_ = e / 3, c = e % 3;
+      const int yy = 2 * y0 - 3 + r, xx = 2 * x0 - 3 + px_;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        v = __ldg(img + c * plane + (long long)yy * W + xx);
+        if (normalize) v = __fsub_rn(__fmul_rn(v, (float)(2 / 255.)), 1.f);       // core/raft.py:40-41
+      }
+    }
+    sP[i] = __float2half_rn(v);
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * C1_WPITCH + 8 * (lane >> 4)) * 2;
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+    const __half* prow = sP + (2 * warp + ky) * C1_PITCH;
+#pragma unroll
+    for (int k16 = 0; k16 < 2; ++k16) {
+      // A fragment: rows g / g + 8 = output pixels x0 + g / x0 + g + 8 -> patch column 2 * x, i.e. element offset 6 * x
+      const int kk = k16 * 16 + q * 2;
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(prow + 6 * g + kk);
+      a[1] = *reinterpret_cast<const uint32_t*>(prow + 6 * (g + 8) + kk);
+      a[2] = *reinterpret_cast<const uint32_t*>(prow + 6 * g + kk + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(prow + 6 * (g + 8) + kk + 8);
+#pragma unroll
+      for (int jp = 0; jp < 2; ++jp) {
+        uint32_t b[4];
+        e_ldmatrix_x4_trans(b, bBase + ((ky * 32 + k16 * 16) * C1_WPITCH + jp * 16) * 2);
+        e_mma16816(acc[2 * jp], a, b[0], b[1]);
+        e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+      }
+    }
+  }
+  conv_epilogue<32>(acc, bias, out, ow, oh, x0, y0 + warp, lane, warp, stats_part, sred);
+}
+
+// ---- 3x3 convs ------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int STRIDE>
+struct C3 {
+  static constexpr int HW_ = STRIDE * (ETW - 1) + 3, HH_ = STRIDE * (ETH - 1) + 3;     // halo tile
+  static constexpr int APITCH = CIN + 8, WPITCH = COUT + 8;                            // halfs
+  static constexpr int A_BYTES = HW_ * HH_ * APITCH * 2;
+  static constexpr int W_BYTES = 9 * CIN * WPITCH * 2;
+  static constexpr int SMEM = A_BYTES + W_BYTES + 8 * COUT * 2 * 4;
+};
+
+template <int CIN, int COUT, int STRIDE>
+__global__ void __launch_bounds__(256) enc_conv3x3_kernel(const __half* __restrict__ in, int ih, int iw,
+                                                          const __half* __restrict__ wk /* [9][CIN][COUT] */,
+                                                          const float* __restrict__ bias, __half* __restrict__ out,
+                                                          int oh, int ow, float* __restrict__ stats_part) {
+  using S = C3<CIN, COUT, STRIDE>;
+  extern __shared__ __align__(128) unsigned char esm[];
+  const uint32_t sA = smem_u32(esm), sW = sA + S::A_BYTES;
+  float* sred = reinterpret_cast<float*>(esm + S::A_BYTES + S::W_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_x = (ow + ETW - 1) / ETW;
+  const int x0 = (blockIdx.x % tiles_x) * ETW, y0 = (blockIdx.x / tiles_x) * ETH;
+  constexpr int CPP = CIN / 8;              // 16-byte pieces per pixel
+  for (int i = tid; i < S::HW_ * S::HH_ * CPP; i += 256) {
+    const int hp = i / CPP, c = i % CPP;
+    const int yy = STRIDE * y0 - 1 + hp / S::HW_, xx = STRIDE * x0 - 1 + hp % S::HW_;
+    const bool ok = yy >= 0 && yy < ih && xx >= 0 && xx < iw;
+    e_cp_async16(sA + (hp * S::APITCH + c * 8) * 2, in + ((long long)(ok ? yy : 0) * iw + (ok ? xx : 0)) * CIN + c * 8, ok);
+  }
+  constexpr int WPR = COUT / 8;
+  for (int i = tid; i < 9 * CIN * WPR; i += 256) {
+    const int k = i / WPR, c = i % WPR;
+    e_cp_async16(sW + (k * S::WPITCH + c * 8) * 2, wk + (long long)k * COUT + c * 8, true);
+  }
+  e_cp_async_commit();
+  e_cp_async_wait_all();
+  __syncthreads();
+  float acc[COUT / 8][4];
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lcol = 8 * (lane >> 4);
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    // ldmatrix row of this lane: output pixel x = lrow of tile row `warp` -> halo pixel (STRIDE*warp + ky, STRIDE*x + kx)
+    const uint32_t aRow = sA + (((STRIDE * warp + ky) * S::HW_ + STRIDE * lrow + kx) * S::APITCH + lcol) * 2;
+    const uint32_t bRow = sW + ((tap * CIN + lrow) * S::WPITCH + lcol) * 2;
+#pragma unroll
+    for (int k16 = 0; k16 < CIN / 16; ++k16) {
+      uint32_t a[4];
+      e_ldmatrix_x4(a, aRow + k16 * 32);
+#pragma unroll
+      for (int jp = 0; jp < COUT / 16; ++jp) {
+        uint32_t b[4];
+        e_ldmatrix_x4_trans(b, bRow + (k16 * 16 * S::WPITCH + jp * 16) * 2);
+        e_mma16816(acc[2 * jp], a, b[0], b[1]);
+        e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+      }
+    }
+  }
+  conv_epilogue<COUT>(acc, bias, out, ow, oh, x0, y0 + warp, lane, warp, stats_part, sred);
+}
+
+// ---- 1x1 convs ------------------------------------------------------------------------------------------------------
+// MODE 0: raw fp16 NHWC + stats (down-sample branch, stride 2).
+// MODE 1: final conv of fnet: out_nhwc (scaled by `scale`) and / or out_nchw (unscaled), fp16.
+// MODE 2: final conv of cnet (COUT = 128): net = tanh(ch 0..63), inp = relu(ch 64..127) (core/raft.py:58-60), NHWC
+//         ([px][64] each) and / or NCHW.
+template <int CIN, int COUT, int STRIDE, int MODE>
+struct C1x1 {
+  static constexpr int APITCH = CIN + 8, WPITCH = COUT + 8;
+  static constexpr int A_BYTES = ETW * ETH * APITCH * 2;
+  static constexpr int W_BYTES = CIN * WPITCH * 2;
+  static constexpr int SMEM = A_BYTES + W_BYTES + 8 * COUT * 2 * 4;
+};
+
+template <int CIN, int COUT, int STRIDE, int MODE>
+__global__ void __launch_bounds__(256) enc_conv1x1_kernel(const __half* __restrict__ in, int ih, int iw,
+                                                          const __half* __restrict__ wk /* [CIN][COUT] */,
+                                                          const float* __restrict__ bias, __half* __restrict__ out_nhwc,
+                                                          __half* __restrict__ out_nhwc2, __half* __restrict__ out_nchw,
+                                                          float scale, int oh, int ow, float* __restrict__ stats_part) {
+  using S = C1x1<CIN, COUT, STRIDE, MODE>;
+  extern __shared__ __align__(128) unsigned char esm[];
+  const uint32_t sA = smem_u32(esm), sW = sA + S::A_BYTES;
+  float* sred = reinterpret_cast<float*>(esm + S::A_BYTES + S::W_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_x = (ow + ETW - 1) / ETW;
+  const int x0 = (blockIdx.x % tiles_x) * ETW, y0 = (blockIdx.x / tiles_x) * ETH;
+  constexpr int CPP = CIN / 8;
+  for (int i = tid; i < ETW * ETH * CPP; i += 256) {
+    const int hp = i / CPP, c = i % CPP;
+    const int yy = STRIDE * (y0 + hp / ETW), xx = STRIDE * (x0 + hp % ETW);
+    const bool ok = yy < ih && xx < iw;
+    e_cp_async16(sA + (hp * S::APITCH + c * 8) * 2, in + ((long long)(ok ? yy : 0) * iw + (ok ? xx : 0)) * CIN + c * 8, ok);
+  }
+  constexpr int WPR = COUT / 8;
+  for (int i = tid; i < CIN * WPR; i += 256) {
+    const int k = i / WPR, c = i % WPR;
+    e_cp_async16(sW + (k * S::WPITCH + c * 8) * 2, wk + (long long)k * COUT + c * 8, true);
+  }
+  e_cp_async_commit();
+  e_cp_async_wait_all();
+  __syncthreads();
+  float acc[COUT / 8][4];
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lcol = 8 * (lane >> 4);
+  const uint32_t aRow = sA + ((warp * ETW + lrow) * S::APITCH + lcol) * 2;
+  const uint32_t bRow = sW + (lrow * S::WPITCH + lcol) * 2;
+#pragma unroll
+  for (int k16 = 0; k16 < CIN / 16; ++k16) {
+    uint32_t a[4];
+    e_ldmatrix_x4(a, aRow + k16 * 32);
+#pragma unroll
+    for (int jp = 0; jp < COUT / 16; ++jp) {
+      uint32_t b[4];
+      e_ldmatrix_x4_trans(b, bRow + (k16 * 16 * S::WPITCH + jp * 16) * 2);
+      e_mma16816(acc[2 * jp], a, b[0], b[1]);
+      e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+  }
+  if (MODE == 0) {
+    conv_epilogue<COUT>(acc, bias, out_nhwc, ow, oh, x0, y0 + warp, lane, warp, stats_part, sred);
+    return;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  const int y = y0 + warp;
+  if (y >= oh) return;
+  const long long opx = (long long)oh * ow;
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j) {
+    const int n = j * 8 + q * 2;
+    const float b0 = __ldg(bias + n), b1 = __ldg(bias + n + 1);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int x = x0 + g + 8 * half;
+      if (x >= ow) continue;
+      const long long p = (long long)y * ow + x;
+      float v0 = h_round(acc[j][2 * half] + b0), v1 = h_round(acc[j][2 * half + 1] + b1);     // conv output, fp16
+      if (MODE == 1) {
+        if (out_nchw) {
+          out_nchw[(long long)n * opx + p] = __float2half_rn(v0);
+          out_nchw[(long long)(n + 1) * opx + p] = __float2half_rn(v1);
+        }
+        if (out_nhwc) *reinterpret_cast<__half2*>(out_nhwc + p * COUT + n) = __floats2half2_rn(v0 * scale, v1 * scale);
+      } else {
+        // split (core/raft.py:58-60): tanh / relu on fp16 values, fp16 results
+        const bool is_net = n < 64;
+        v0 = is_net ? h_round(tanhf(v0)) : fmaxf(v0, 0.f);
+        v1 = is_net ? h_round(tanhf(v1)) : fmaxf(v1, 0.f);
+        const int c = is_net ? n : n - 64;
+        __half* nh = is_net ? out_nhwc : out_nhwc2;
+        if (nh) *reinterpret_cast<__half2*>(nh + p * 64 + c) = __floats2half2_rn(v0, v1);
+        if (out_nchw) {      // [2][64][px]: net planes then inp planes
+          out_nchw[(long long)n * opx + p] = __float2half_rn(v0);
+          out_nchw[(long long)(n + 1) * opx + p] = __float2half_rn(v1);
+        }
+      }
+    }
+  }
+}
+
+// ---- instance-norm statistics: partial sums of all CTAs -> mean, rstd per channel (one block per channel) ----
+__global__ void __launch_bounds__(256) enc_stats_kernel(const float* __restrict__ part, int n_cta, int C, long long count,
+                                                        float* __restrict__ mean_rstd /* [C][2] */) {
+  __shared__ double s0[256], s1[256];
+  const int c = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n_cta; i += 256) {
+    a += (double)part[((long long)i * C + c) * 2];
+    b += (double)part[((long long)i * C + c) * 2 + 1];
+  }
+  s0[threadIdx.x] = a;
+  s1[threadIdx.x] = b;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      s0[threadIdx.x] += s0[threadIdx.x + st];
+      s1[threadIdx.x] += s1[threadIdx.x + st];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double m = s0[0] / (double)count;
+    double var = s1[0] / (double)count - m * m;          // biased variance (F.instance_norm)
+    var = var < 0.0 ? 0.0 : var;
+    mean_rstd[2 * c] = (float)m;
+    mean_rstd[2 * c + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+}
+
+// ---- the element-wise structure of ResidualBlock.forward (core/extractor.py:50-58) ----
+//   out = relu(norm_a(a))                               (b == nullptr)
+//   out = relu(b + relu(norm_a(a)))                     (b given, stats_b == nullptr: identity shortcut)
+//   out = relu(norm_b(b) + relu(norm_a(a)))             (b and stats_b given: down-sample shortcut)
+// stats == nullptr (cnet, norm_fn 'none'): the norm is the identity.  fp16 in / out, fp16 rounding after the norm, after
+// the inner relu (no-op) and after the sum, like the reference's fp16 tensors.
+__global__ void __launch_bounds__(256) enc_norm_kernel(const __half* __restrict__ a, const float* __restrict__ stats_a,
+                                                       const __half* __restrict__ b, const float* __restrict__ stats_b,
+                                                       __half* __restrict__ out, long long n_vec8, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec8) return;
+  const int c0 = (int)((i * 8) % C);
+  const uint4 av = __ldg(reinterpret_cast<const uint4*>(a) + i);
+  uint4 bv = make_uint4(0, 0, 0, 0);
+  if (b) bv = __ldg(reinterpret_cast<const uint4*>(b) + i);
+  const __half* ah = reinterpret_cast<const __half*>(&av);
+  const __half* bh = reinterpret_cast<const __half*>(&bv);
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float x = __half2float(ah[e]);
+    if (stats_a) x = h_round((x - __ldg(stats_a + 2 * (c0 + e))) * __ldg(stats_a + 2 * (c0 + e) + 1));
+    x = fmaxf(x, 0.f);
+    if (b) {
+      float y = __half2float(bh[e]);
+      if (stats_b) y = h_round((y - __ldg(stats_b + 2 * (c0 + e))) * __ldg(stats_b + 2 * (c0 + e) + 1));
+      x = fmaxf(h_round(x + y), 0.f);
+    }
+    o[e] = __float2half_rn(x);
+  }
+  *(reinterpret_cast<uint4*>(out) + i) = *reinterpret_cast<const uint4*>(o);
+}
+
+// ---- weight blob -----------------------------------------------------------------------------------------------------
+// fp16 weights in the kernels' k-major layouts, fp32 biases (rounded to fp16 values like autocast's bias cast):
+//   conv1 [7][32][32]: k = kx*3 + c for k < 21, zero above    each 3x3: [9][CIN][COUT]    each 1x1: [CIN][COUT]
+struct EncLayout {
+  size_t conv1_w, conv1_b;
+  size_t l1_w[4], l1_b[4];              // layer1.{0,1}.conv{1,2}
+  size_t l2a_w[2], l2a_b[2];            // layer2.0.conv1 (32->64 s2), conv2
+  size_t l2d_w, l2d_b;                  // layer2.0.downsample.0 (1x1 s2)
+  size_t l2b_w[2], l2b_b[2];            // layer2.1.conv1, conv2
+  size_t conv2_w, conv2_b;              // final 1x1 (64 -> out_dim)
+  size_t total;
+};
+static EncLayout enc_layout(int out_dim) {
+  EncLayout L{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+  L.conv1_w = take(7 * 32 * 32 * 2); L.conv1_b = take(32 * 4);
+  for (int i = 0; i < 4; ++i) { L.l1_w[i] = take(9 * 32 * 32 * 2); L.l1_b[i] = take(32 * 4); }
+  L.l2a_w[0] = take(9 * 32 * 64 * 2); L.l2a_b[0] = take(64 * 4);
+  L.l2a_w[1] = take(9 * 64 * 64 * 2); L.l2a_b[1] = take(64 * 4);
+  L.l2d_w = take(32 * 64 * 2); L.l2d_b = take(64 * 4);
+  for (int i = 0; i < 2; ++i) { L.l2b_w[i] = take(9 * 64 * 64 * 2); L.l2b_b[i] = take(64 * 4); }
+  L.conv2_w = take((size_t)64 * out_dim * 2); L.conv2_b = take((size_t)out_dim * 4);
+  L.total = o;
+  return L;
+}
+
+struct EncWs {
+  __half *t0, *t1, *t2, *t3;            // half-resolution tensors [h2*w2][32]
+  __half *u0, *u1, *u2, *u3;            // quarter-resolution tensors [h4*w4][64]
+  float* part;                          // per-CTA partial sums (largest conv)
+  float* stats[3];                      // mean / rstd of up to three norms in flight
+  size_t total;
+};
+static EncWs enc_carve(void* base, int H, int W) {
+  const int h2 = (H + 1) / 2, w2 = (W + 1) / 2, h4 = (h2 + 1) / 2, w4 = (w2 + 1) / 2;
+  const long long p2 = (long long)h2 * w2, p4 = (long long)h4 * w4;
+  EncWs w{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return (char*)base + r; };
+  w.t0 = (__half*)take(p2 * 32 * 2); w.t1 = (__half*)take(p2 * 32 * 2);
+  w.t2 = (__half*)take(p2 * 32 * 2); w.t3 = (__half*)take(p2 * 32 * 2);
+  w.u0 = (__half*)take(p4 * 64 * 2); w.u1 = (__half*)take(p4 * 64 * 2);
+  w.u2 = (__half*)take(p4 * 64 * 2); w.u3 = (__half*)take(p4 * 64 * 2);
+  const long long n_cta2 = (long long)((w2 + ETW - 1) / ETW) * ((h2 + ETH - 1) / ETH);
+  w.part = (float*)take(n_cta2 * 64 * 2 * 4);
+  for (int i = 0; i < 3; ++i) w.stats[i] = (float*)take(64 * 2 * 4);
+  w.total = o;
+  return w;
+}
+
+template <int CIN, int COUT, int STRIDE>
+static int launch_conv3x3(const __half* in, int ih, int iw, const __half* wk, const float* bias, __half* out, int oh, int ow,
+                          float* part, cudaStream_t stream) {
+  using S = C3<CIN, COUT, STRIDE>;
+  static std::atomic<unsigned long long> configured{0};
+  if (first_time_on_device(configured))
+    CER_CUDA(cudaFuncSetAttribute(enc_conv3x3_kernel<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+  const int grid = ((ow + ETW - 1) / ETW) * ((oh + ETH - 1) / ETH);
+  CER_LAUNCH(KK_LAYOUT, (enc_conv3x3_kernel<CIN, COUT, STRIDE>), grid, 256, S::SMEM, stream, in, ih, iw, wk, bias, out, oh, ow,
+             part);
+  return check_launch("enc_conv3x3");
+}
+
+template <int CIN, int COUT, int STRIDE, int MODE>
+static int launch_conv1x1(const __half* in, int ih, int iw, const __half* wk, const float* bias, __half* o_nhwc,
+                          __half* o_nhwc2, __half* o_nchw, float scale, int oh, int ow, float* part, cudaStream_t stream) {
+  using S = C1x1<CIN, COUT, STRIDE, MODE>;
+  static std::atomic<unsigned long long> configured{0};
+  if (first_time_on_device(configured))
+    CER_CUDA(cudaFuncSetAttribute(enc_conv1x1_kernel<CIN, COUT, STRIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  S::SMEM));
+  const int grid = ((ow + ETW - 1) / ETW) * ((oh + ETH - 1) / ETH);
+  CER_LAUNCH(KK_LAYOUT, (enc_conv1x1_kernel<CIN, COUT, STRIDE, MODE>), grid, 256, S::SMEM, stream, in, ih, iw, wk, bias,
+             o_nhwc, o_nhwc2, o_nchw, scale, oh, ow, part);
+  return check_launch("enc_conv1x1");
+}
+
+static int launch_stats(const float* part, int n_cta, int C, long long count, float* out, cudaStream_t stream) {
+  CER_LAUNCH(KK_LAYOUT, enc_stats_kernel, C, 256, 0, stream, part, n_cta, C, count, out);
+  return check_launch("enc_stats");
+}
+static int launch_norm(const __half* a, const float* sa, const __half* b, const float* sb, __half* out, long long n, int C,
+                       cudaStream_t stream) {
+  const long long nv = n / 8;
+  CER_LAUNCH(KK_LAYOUT, enc_norm_kernel, ceil_div(nv, 256), 256, 0, stream, a, sa, b, sb, out, nv, C);
+  return check_launch("enc_norm");
+}
+
+}  // namespace
+}  // namespace cer
+
+using namespace cer;
+
+extern "C" {
+
+size_t cer_encoder_blob_bytes(int out_dim) { return enc_layout(out_dim).total; }
+
+size_t cer_encoder_workspace_bytes(int H, int W) { return enc_carve(nullptr, H, W).total; }
+
+// w: 24 arrays in state-dict order of BasicEncoder (type "HR"), OIHW fp32:
+//   conv1.{weight,bias}; layer1.{0,1}.conv{1,2}.{weight,bias}; layer2.0.conv1, layer2.0.conv2, layer2.0.downsample.0,
+//   layer2.1.conv1, layer2.1.conv2 ({weight,bias} each); conv2.{weight,bias}
+int cer_pack_encoder_weights(const float* const* w, int out_dim, void* blob_host) {
+  CER_REQUIRE(w && blob_host && (out_dim == 64 || out_dim == 128), "cer_pack_encoder_weights: bad arguments");
+  const EncLayout L = enc_layout(out_dim);
+  char* B = (char*)blob_host;
+  memset(B, 0, L.total);
+  auto bias = [&](size_t off, const float* src, int n) {
+    float* d = (float*)(B + off);
+    for (int i = 0; i < n; ++i) d[i] = __half2float(__float2half_rn(src[i]));
+  };
+  auto kxk = [&](size_t off, const float* src, int cout, int cin, int k) {     // OIHW -> [tap][cin][cout]
+    __half* d = (__half*)(B + off);
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < k * k; ++t)
+          d[((size_t)t * cin + c) * cout + o] = __float2half_rn(src[((size_t)o * cin + c) * k * k + t]);
+  };
+  int i = 0;
+  {  // conv1: [ky][k = kx*3 + c (21 of 32)][32]
+    const float* src = w[i++];
+    __half* d = (__half*)(B + L.conv1_w);
+    for (int o = 0; o < 32; ++o)
+      for (int c = 0; c < 3; ++c)
+        for (int ky = 0; ky < 7; ++ky)
+          for (int kx = 0; kx < 7; ++kx)
+            d[((size_t)ky * 32 + kx * 3 + c) * 32 + o] = __float2half_rn(src[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx]);
+    bias(L.conv1_b, w[i++], 32);
+  }
+  for (int b = 0; b < 4; ++b) { kxk(L.l1_w[b], w[i++], 32, 32, 3); bias(L.l1_b[b], w[i++], 32); }
+  kxk(L.l2a_w[0], w[i++], 64, 32, 3); bias(L.l2a_b[0], w[i++], 64);
+  kxk(L.l2a_w[1], w[i++], 64, 64, 3); bias(L.l2a_b[1], w[i++], 64);
+  kxk(L.l2d_w, w[i++], 64, 32, 1); bias(L.l2d_b, w[i++], 64);
+  for (int b = 0; b < 2; ++b) { kxk(L.l2b_w[b], w[i++], 64, 64, 3); bias(L.l2b_b[b], w[i++], 64); }
+  kxk(L.conv2_w, w[i++], out_dim, 64, 1); bias(L.conv2_b, w[i++], out_dim);
+  return CER_OK;
+}
+
+// One image through the encoder.
+//   image [3][H][W] fp32 (0..255 if normalize, else already x*2/255-1), H and W multiples of 4
+//   instance_norm 1: fnet (out_dim 64): out_nhwc [h4*w4][64] fp16 scaled by nhwc_scale (nullable), out_nchw [64][h4*w4]
+//   instance_norm 0: cnet (out_dim 128); context_split 1: out_nhwc = net, out_nhwc2 = inp ([h4*w4][64] each, nullable),
+//                    out_nchw [2][64][h4*w4] = net planes then inp planes (nullable); context_split 0: the raw map,
+//                    out_nchw [128][h4*w4] / out_nhwc [h4*w4][128]
+int cer_encoder_forward(const void* blob, void* workspace, const float* image, int H, int W, int normalize, int out_dim,
+                        int instance_norm, int context_split, void* out_nhwc, void* out_nhwc2, void* out_nchw,
+                        float nhwc_scale, cer_stream_t stream_) {
+  CER_REQUIRE(blob && workspace && image, "cer_encoder_forward: null pointer");
+  CER_REQUIRE(H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "cer_encoder_forward: H and W must be multiples of 4 (core/raft.py:49-50)");
+  CER_REQUIRE((out_dim == 64 && instance_norm) || (out_dim == 128 && !instance_norm),
+              "cer_encoder_forward: fnet (64 channels, instance norm) or cnet (128 channels, no norm)");
+  CER_REQUIRE(out_nhwc || out_nchw || out_nhwc2, "cer_encoder_forward: no output requested");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const EncLayout L = enc_layout(out_dim);
+  const char* B = (const char*)blob;
+  EncWs ws = enc_carve(workspace, H, W);
+  const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4;
+  const long long p2 = (long long)h2 * w2, p4 = (long long)h4 * w4;
+  const int cta2 = ((w2 + ETW - 1) / ETW) * ((h2 + ETH - 1) / ETH), cta4 = ((w4 + ETW - 1) / ETW) * ((h4 + ETH - 1) / ETH);
+  const bool in_ = instance_norm != 0;
+  float* part = in_ ? ws.part : nullptr;
+  auto W16 = [&](size_t off) { return (const __half*)(B + off); };
+  auto F32 = [&](size_t off) { return (const float*)(B + off); };
+  int rc;
+  // norm(conv) helper: statistics of the conv that just ran -> ws.stats[slot]
+  auto stats = [&](int n_cta, int C, long long count, int slot) -> const float* {
+    if (!in_) return nullptr;
+    int r = launch_stats(ws.part, n_cta, C, count, ws.stats[slot], stream);
+    return r ? nullptr : ws.stats[slot];
+  };
+  // conv1 -> norm1 -> relu                                                           (extractor.py:146-148)
+  CER_LAUNCH(KK_LAYOUT, enc_conv1_kernel, cta2, 256, 0, stream, image, H, W, W16(L.conv1_w), F32(L.conv1_b), ws.t0, h2, w2,
+             normalize, part);
+  if ((rc = check_launch("enc_conv1"))) return rc;
+  if ((rc = launch_norm(ws.t0, stats(cta2, 32, p2, 0), nullptr, nullptr, ws.t1, p2 * 32, 32, stream))) return rc;
+  // layer1: two residual blocks @32, stride 1                                        (extractor.py:50-58)
+  __half* x = ws.t1;
+  __half* spare[3] = {ws.t0, ws.t2, ws.t3};
+  for (int blk = 0; blk < 2; ++blk) {
+    __half *a = spare[0], *b = spare[1], *o = spare[2];
+    if ((rc = launch_conv3x3<32, 32, 1>(x, h2, w2, W16(L.l1_w[2 * blk]), F32(L.l1_b[2 * blk]), a, h2, w2, part, stream))) return rc;
+    if ((rc = launch_norm(a, stats(cta2, 32, p2, 0), nullptr, nullptr, b, p2 * 32, 32, stream))) return rc;
+    if ((rc = launch_conv3x3<32, 32, 1>(b, h2, w2, W16(L.l1_w[2 * blk + 1]), F32(L.l1_b[2 * blk + 1]), a, h2, w2, part, stream))) return rc;
+    if ((rc = launch_norm(a, stats(cta2, 32, p2, 0), x, nullptr, o, p2 * 32, 32, stream))) return rc;
+    spare[2] = x;
+    x = o;
+  }
+  // layer2.0: 32 -> 64, stride 2, down-sample shortcut
+  if ((rc = launch_conv3x3<32, 64, 2>(x, h2, w2, W16(L.l2a_w[0]), F32(L.l2a_b[0]), ws.u0, h4, w4, part, stream))) return rc;
+  if ((rc = launch_norm(ws.u0, stats(cta4, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2a_w[1]), F32(L.l2a_b[1]), ws.u0, h4, w4, part, stream))) return rc;
+  const float* s_b = stats(cta4, 64, p4, 0);
+  if ((rc = launch_conv1x1<32, 64, 2, 0>(x, h2, w2, W16(L.l2d_w), F32(L.l2d_b), ws.u2, nullptr, nullptr, 1.f, h4, w4, part, stream))) return rc;
+  const float* s_d = stats(cta4, 64, p4, 1);
+  if ((rc = launch_norm(ws.u0, s_b, ws.u2, in_ ? s_d : nullptr, ws.u3, p4 * 64, 64, stream))) return rc;
+  // layer2.1: 64 -> 64
+  if ((rc = launch_conv3x3<64, 64, 1>(ws.u3, h4, w4, W16(L.l2b_w[0]), F32(L.l2b_b[0]), ws.u0, h4, w4, part, stream))) return rc;
+  if ((rc = launch_norm(ws.u0, stats(cta4, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2b_w[1]), F32(L.l2b_b[1]), ws.u0, h4, w4, part, stream))) return rc;
+  if ((rc = launch_norm(ws.u0, stats(cta4, 64, p4, 0), ws.u3, nullptr, ws.u2, p4 * 64, 64, stream))) return rc;
+  // conv2 (1x1) and the output layouts
+  if (out_dim == 64)
+    return launch_conv1x1<64, 64, 1, 1>(ws.u2, h4, w4, W16(L.conv2_w), F32(L.conv2_b), (__half*)out_nhwc, nullptr,
+                                        (__half*)out_nchw, nhwc_scale, h4, w4, nullptr, stream);
+  if (!context_split)      // the raw 128-channel map the reference's cnet returns (core/raft.py:57)
+    return launch_conv1x1<64, 128, 1, 1>(ws.u2, h4, w4, W16(L.conv2_w), F32(L.conv2_b), (__half*)out_nhwc, nullptr,
+                                         (__half*)out_nchw, nhwc_scale, h4, w4, nullptr, stream);
+  return launch_conv1x1<64, 128, 1, 2>(ws.u2, h4, w4, W16(L.conv2_w), F32(L.conv2_b), (__half*)out_nhwc, (__half*)out_nhwc2,
+                                       (__half*)out_nchw, 1.f, h4, w4, nullptr, stream);
+}
+
+}  // extern "C"

@@ -111,3 +111,107 @@ def fuse_depth_maps(all_depths, all_intrinsics, all_extrinsics, pair_data, glb=0
         if images is not None:
             colors.append((images[ref_view][valid] * 255).to(torch.uint8))
     return {"thre": thre, "ratios": ratios, "masks": masks, "depth_est": depth_est, "points": points, "colors": colors}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# File layer of the reference's fusion() (fusion.py:110-200, 256-318): depth maps from PFM files, images and cameras
+# from the data loader, masks to PNG, the fused point cloud to result.ply.  Host I/O by nature (cv2 / numpy for the
+# files and the bilinear image resize, like the reference); the geometry runs on the GPU through fuse_depth_maps.
+# ------------------------------------------------------------------------------------------------------------
+def write_ply(path, xyz, rgb):
+    """Point cloud -> binary little-endian PLY with the element / property layout plyfile writes for the reference's
+    structured array (fusion.py:304-316): vertex {float x, y, z; uchar red, green, blue}."""
+    import numpy as np
+    xyz = np.ascontiguousarray(np.asarray(xyz, dtype="<f4").reshape(-1, 3))
+    rgb = np.ascontiguousarray(np.asarray(rgb, dtype=np.uint8).reshape(-1, 3))
+    if len(xyz) != len(rgb):
+        raise RuntimeError("write_ply: one colour per point expected")
+    rec = np.empty(len(xyz), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    for i, n in enumerate(("x", "y", "z")):
+        rec[n] = xyz[:, i]
+    for i, n in enumerate(("red", "green", "blue")):
+        rec[n] = rgb[:, i]
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+              "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n" % len(rec))
+    with open(path, "wb") as f:
+        f.write(header.encode("ascii"))
+        f.write(rec.tobytes())
+
+
+def _fit_image_to_depth(img, depth_hw, K):
+    """fusion.py:150-171: bring the colour image to the depth map's size -- uniform scale so that one side matches, then
+    a centred crop of the other -- and move the intrinsics with it.  img: H x W x 3 in 0..1; returns (image, K)."""
+    import math
+    import cv2
+    dh, dw = depth_hw
+    ih, iw = img.shape[:2]
+    scale = float(dh) / ih                    # match the heights ...
+    crop_rows = False
+    if dw / iw > scale:                       # ... unless the depth map is relatively wider: match the widths
+        scale = float(dw) / iw
+        crop_rows = True
+    img = cv2.resize(img, None, fx=scale, fy=scale, interpolation=cv2.INTER_LINEAR)
+    K = K.copy()
+    K[:2, :] *= scale
+    if not crop_rows:
+        off = int(math.ceil((img.shape[1] - dw) / 2))
+        img = img[:, off:dw + off, :]
+        K[0, 2] -= off
+    else:
+        off = int(math.ceil((img.shape[0] - dh) / 2))
+        img = img[off:img.shape[0] - off, :, :]
+        K[1, 2] -= off
+    return img, K
+
+
+def fusion(data_loader, output_folder, suffix="", glb=0.25, rescale=1, device=None):
+    """Drop-in for the reference's ``fusion()`` (fusion.py:110-318), same arguments and the same files written:
+    ``mask/{view}{suffix}.png`` per reference view and ``result.ply``.  ``data_loader`` yields
+    (images [1,n,3,H,W] 0..255, extrinsics [1,n,4,4], intrinsics [1,n,3,3], image_names, _) with the reference view
+    first; the depth maps are read from ``output_folder/depths/{name}{suffix}.pfm``.
+    Returns the dict of fuse_depth_maps (threshold, masks, averaged depths, points, colours)."""
+    import os
+    from pathlib import Path
+
+    import cv2
+    import numpy as np
+
+    from .prep import readPFM
+    output_folder = Path(output_folder)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    name_to_index, pairs = {}, []
+    imgs, depths, Ks, Es = [], [], [], []
+    for i, (images, extrinsics, intrinsics, image_names, _) in enumerate(data_loader):
+        ref_name = image_names[0][0]
+        name_to_index[ref_name] = i
+        pairs.append((ref_name, [x[0] for x in image_names[1:]]))
+        img = images.squeeze(0)[0].permute(1, 2, 0).numpy() / 255.
+        depth = np.ascontiguousarray(readPFM(output_folder / "depths" / f"{ref_name}{suffix}.pfm"))
+        dh, dw = depth.shape
+        depth = cv2.resize(depth, (int(dw * rescale), int(dh * rescale)))            # fusion.py:148
+        img, K = _fit_image_to_depth(img, depth.shape, np.array(intrinsics[0][0], dtype=np.float64))
+        if i > 0 and (img.shape != imgs[0].shape or depth.shape != depths[0].shape):
+            # fusion.py:184-196: views of another size are copied into the first view's frame (top-left aligned)
+            fi, fd = np.zeros_like(imgs[0]), np.zeros_like(depths[0])
+            sh, sw = min(img.shape[0], fi.shape[0]), min(img.shape[1], fi.shape[1])
+            fi[:sh, :sw] = img[:sh, :sw]
+            sh, sw = min(depth.shape[0], fd.shape[0]), min(depth.shape[1], fd.shape[1])
+            fd[:sh, :sw] = depth[:sh, :sw]
+            img, depth = fi, fd
+        imgs.append(img)
+        depths.append(depth)
+        Ks.append(K)
+        Es.append(np.array(extrinsics[0][0], dtype=np.float64))
+    pair_idx = [(name_to_index[r], [name_to_index[s] for s in srcs]) for r, srcs in pairs]
+    t = torch.from_numpy
+    images_t = t(np.stack(imgs)).to(dev)
+    out = fuse_depth_maps(t(np.stack(depths)).float().to(dev), t(np.stack(Ks)).float().to(dev),
+                          t(np.stack(Es)).float().to(dev), pair_idx, glb=glb, images=images_t)
+    os.makedirs(output_folder / "mask", exist_ok=True)
+    for ref_view, _ in pair_idx:
+        cv2.imwrite(str(output_folder / "mask" / f"{ref_view}{suffix}.png"),
+                    out["masks"][ref_view].cpu().numpy().astype(np.uint8) * 255)
+    xyz = torch.cat(out["points"], 0).cpu().numpy()
+    rgb = torch.cat(out["colors"], 0).cpu().numpy()
+    write_ply(output_folder / "result.ply", xyz, rgb)
+    return out

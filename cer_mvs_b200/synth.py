@@ -182,3 +182,37 @@ def make_scene(height, width, num_src, seed=0, fp16_exact=True):
     net, inp = make_context(height // 4, width // 4, seed=seed, fp16_exact=fp16_exact)
     return dict(fmaps=fmaps, net=net, inp=inp, poses=poses[None], intrinsics=K[None],
                 true_disp=true_disp)
+
+
+def make_encoder_weights(seed: int = 0, out_dim: int = 64, fp16_exact: bool = True):
+    """State dict (numpy, OIHW float32) for the reference ``BasicEncoder`` of type "HR" (core/extractor.py:62-118):
+    Kaiming-normal weights (fan_out, relu) like its own init, small random biases."""
+    rs = np.random.RandomState(seed + 4000)
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        std = np.sqrt(2.0 / (cout * k * k))
+        sd[name + ".weight"] = (rs.standard_normal((cout, cin, k, k)) * std).astype(np.float32)
+        sd[name + ".bias"] = (rs.standard_normal((cout,)) * 0.05).astype(np.float32)
+
+    conv("conv1", 32, 3, 7)
+    for b in (0, 1):
+        conv(f"layer1.{b}.conv1", 32, 32, 3)
+        conv(f"layer1.{b}.conv2", 32, 32, 3)
+    conv("layer2.0.conv1", 64, 32, 3)
+    conv("layer2.0.conv2", 64, 64, 3)
+    conv("layer2.0.downsample.0", 64, 32, 1)
+    conv("layer2.1.conv1", 64, 64, 3)
+    conv("layer2.1.conv2", 64, 64, 3)
+    conv("conv2", out_dim, 64, 1)
+    if fp16_exact:
+        sd = {k: v.astype(np.float16).astype(np.float32) for k, v in sd.items()}
+    return sd
+
+
+def make_image(height, width, n=1, seed=0):
+    """[n,3,H,W] float32 in 0..255: low-passed uniform noise (neighbouring pixels correlate like a photograph)."""
+    rs = np.random.RandomState(seed + 5000)
+    img = rs.uniform(0, 255, (n, 3, height, width))
+    img = (img + np.roll(img, 1, 2) + np.roll(img, 1, 3) + np.roll(img, (1, 1), (2, 3))) / 4
+    return np.ascontiguousarray(img, dtype=np.float32)

@@ -100,6 +100,24 @@ int cer_debug_set_build_profile(unsigned long long* dev_counters);
 /* avg_pool2d([1,2]) pyramid level (core/corr.py:95-97): src [rows, W] -> dst [rows, W/2] (floor). */
 int cer_pool_pairs(const float* src, float* dst, long long rows, int W, cer_stream_t stream);
 
+/* ---- BasicEncoder, type "HR" (core/extractor.py:62-155; fnet / cnet of core/raft.py:28-29,57,66-69) --------------
+ * the producer of the hot path's inputs.  mma.sync implicit-GEMM convolutions on NHWC fp16
+ * activations, instance-norm statistics in fp32, autocast rounding points (csrc/encoder.cu).
+ * Weights: 22 arrays in state-dict order (conv1, layer1.{0,1}.conv{1,2}, layer2.0.{conv1,conv2,downsample.0},
+ * layer2.1.{conv1,conv2}, conv2; weight then bias each), OIHW fp32. */
+size_t cer_encoder_blob_bytes(int out_dim);
+size_t cer_encoder_workspace_bytes(int H, int W);
+int cer_pack_encoder_weights(const float* const* w, int out_dim, void* blob_host);
+/* One image [3][H][W] fp32 (normalize != 0: 0..255 input, x*2/255-1 applied first, core/raft.py:40-41).
+ *   fnet (out_dim 64, instance_norm 1): out_nhwc [H/4*W/4][64] fp16 scaled by nhwc_scale (the build's layout; nullable),
+ *        out_nchw [64][H/4*W/4] fp16 (what the reference module returns; nullable)
+ *   cnet (out_dim 128, instance_norm 0), context_split 1: net = tanh(ch 0..63), inp = relu(ch 64..127)
+ *        (core/raft.py:58-60): out_nhwc = net, out_nhwc2 = inp ([H/4*W/4][64] fp16 each; nullable), out_nchw
+ *        [2][64][H/4*W/4] (nullable); context_split 0: the raw 128-channel map (out_nchw [128][..] / out_nhwc [..][128]) */
+int cer_encoder_forward(const void* blob, void* workspace, const float* image, int H, int W, int normalize, int out_dim,
+                        int instance_norm, int context_split, void* out_nhwc, void* out_nhwc2, void* out_nchw,
+                        float nhwc_scale, cer_stream_t stream);
+
 /* ---- CorrBlock.__call__ (core/corr.py:102-143 + utils/bilinear_sampler.py:6-25) -------------
  * volume [slots, h*w, D] level 0 (levels 1..L-1 are rebuilt on the fly), origin [h*w], zinv [h*w]
  * -> out [slots, L*(2r+1), h, w] fp32 (channel = level*(2r+1) + tap).  L <= 3 needs D >= 4. */

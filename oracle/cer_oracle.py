@@ -294,3 +294,48 @@ def hot_path(sd, fmaps, net, inp, poses, intrinsics, cascade=((64, 64, 8), (-1, 
 
 def to_torch_sd(sd_np):
     return {k: torch.from_numpy(v).float() for k, v in sd_np.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+# BasicEncoder, type "HR" (core/extractor.py:62-155), SURVEY.md section 8f row 1
+# ----------------------------------------------------------------------------------------------
+def _enc_conv(x, sd, name, stride, autocast):
+    w, b = sd[name + ".weight"], sd[name + ".bias"]
+    pad = w.shape[-1] // 2
+    if autocast:
+        return _h(F.conv2d(_h(x), _h(w), _h(b), stride=stride, padding=pad))
+    return F.conv2d(x, w, b, stride=stride, padding=pad)
+
+
+def _enc_norm(x, instance, autocast):
+    """nn.InstanceNorm2d defaults (extractor.py:29,74): no affine, no running stats, eps 1e-5, biased variance."""
+    if not instance:
+        return x
+    y = F.instance_norm(x, eps=1e-5)
+    return _h(y) if autocast else y
+
+
+def _enc_block(x, sd, prefix, stride, instance, autocast):
+    """ResidualBlock.forward (extractor.py:50-58)."""
+    rnd = _h if autocast else (lambda v: v)
+    y = torch.relu(_enc_norm(_enc_conv(x, sd, prefix + ".conv1", stride, autocast), instance, autocast))
+    y = torch.relu(_enc_norm(_enc_conv(y, sd, prefix + ".conv2", 1, autocast), instance, autocast))
+    if stride != 1:
+        x = _enc_norm(_enc_conv(x, sd, prefix + ".downsample.0", stride, autocast), instance, autocast)
+    return torch.relu(rnd(x + y))
+
+
+def basic_encoder(sd, x, instance_norm, autocast=False):
+    """x [N,3,H,W] (already normalised, core/raft.py:40-41) -> [N,out_dim,H/4,W/4]  (extractor.py:143-155)."""
+    x = torch.relu(_enc_norm(_enc_conv(x, sd, "conv1", 2, autocast), instance_norm, autocast))
+    x = _enc_block(x, sd, "layer1.0", 1, instance_norm, autocast)
+    x = _enc_block(x, sd, "layer1.1", 1, instance_norm, autocast)
+    x = _enc_block(x, sd, "layer2.0", 2, instance_norm, autocast)
+    x = _enc_block(x, sd, "layer2.1", 1, instance_norm, autocast)
+    return _enc_conv(x, sd, "conv2", 1, autocast)
+
+
+def context_split(net_inp, autocast=False):
+    """core/raft.py:58-60."""
+    rnd = _h if autocast else (lambda v: v)
+    return rnd(torch.tanh(net_inp[:, :64])), torch.relu(net_inp[:, 64:])

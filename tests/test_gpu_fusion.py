@@ -96,3 +96,45 @@ def test_fuse_depth_maps_bisection_loop(golden):
     z = out["depth_est"].cpu().numpy()[0][m[0]]
     np.testing.assert_allclose(p0[:, 2], z, rtol=1e-5)
     np.testing.assert_allclose(p0[:, 0], (us - K[0, 0, 2]) * z / K[0, 0, 0], rtol=1e-4, atol=1e-3)
+
+
+def test_whole_fusion_against_reference_run(golden, tmp_path):
+    """fusion() end to end -- PFM depth maps and images in, mask PNGs and result.ply out -- against a run of the
+    reference's own fusion() on the same files (oracle/gen_golden_fusion_loop.py).  The threshold bisection is
+    discontinuous: a kept fraction next to ``glb`` can send the two runs down different branches of the last bisection
+    steps, so the masks may differ on the pixels such a threshold difference moves (< 2 %)."""
+    import cv2
+    from cer_mvs_b200 import prep
+    g = golden("fusion_loop")
+    depths, K, E, images = g["depths"], g["K"], g["E"], g["images"]
+    n = depths.shape[0]
+    (tmp_path / "depths").mkdir()
+    for i in range(n):
+        prep.write_pfm(tmp_path / "depths" / f"{i}_s.pfm", depths[i])
+    loader = []
+    for row in g["pairs"]:
+        ids = [int(v) for v in row]
+        loader.append((t(images[ids])[None], t(E[ids])[None], t(K[ids])[None], [(str(j),) for j in ids], 1.0))
+    out = fusion_ops.fusion(loader, tmp_path, suffix="_s", glb=float(g["glb"]), rescale=1)
+    masks = np.stack([cv2.imread(str(tmp_path / "mask" / f"{i}_s.png"), cv2.IMREAD_GRAYSCALE) > 0 for i in range(n)])
+    assert np.array_equal(masks, out["masks"].cpu().numpy())
+    diff = (masks != g["masks"]).mean()
+    print(f"fusion(): mask pixels that differ from the reference run: {diff:.4f}; kept {masks.mean():.3f} vs {g['masks'].mean():.3f}")
+    assert diff < 0.02
+    # result.ply: same header layout as the reference's file, the vertices of the commonly kept pixels agree
+    raw = open(tmp_path / "result.ply", "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    ref_header = g["ply_header"].tobytes().decode()
+    got_header = raw[:end].decode()
+    strip = lambda s: "\n".join(l for l in s.split("\n") if not l.startswith("element vertex"))  # noqa: E731
+    assert strip(got_header) == strip(ref_header)
+    dt = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    verts = np.frombuffer(raw[end:], dtype=dt)
+    assert len(verts) == int(masks.sum())
+    # align the two vertex lists through the masks (both are written view by view, row-major inside a view)
+    both = masks & g["masks"]
+    sel_got, sel_ref = both[masks], both[g["masks"]]
+    xyz = np.stack([verts["x"], verts["y"], verts["z"]], 1)[sel_got]
+    np.testing.assert_allclose(xyz, g["ply_xyz"][sel_ref], rtol=2e-3, atol=0.2)      # depth ~600: 0.2 = 3e-4 relative
+    rgb = np.stack([verts["red"], verts["green"], verts["blue"]], 1)[sel_got]
+    assert (np.abs(rgb.astype(int) - g["ply_rgb"][sel_ref].astype(int)) <= 1).mean() > 0.999
