@@ -71,6 +71,10 @@ SIGNATURES = {
                                  c_int, c_int, c_void_p]),
     "cer_plan_build_stage": (c_int, [c_void_p, c_int, c_void_p]),
     "cer_plan_build_stage_units": (c_int, [c_void_p, c_int, c_ll, c_ll, c_void_p]),
+    "cer_plan_feature_buffer": (c_void_p, [c_void_p, c_int]),
+    "cer_plan_net_buffer": (c_void_p, [c_void_p]),
+    "cer_plan_inp_buffer": (c_void_p, [c_void_p]),
+    "cer_plan_prepare_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cer_plan_partial_volume": (c_void_p, [c_void_p, c_int, C.POINTER(c_size_t)]),
     "cer_plan_iterate_stage": (c_int, [c_void_p, c_int, c_void_p]),
     "cer_plan_finish": (c_int, [c_void_p, c_float, c_void_p, c_void_p]),

@@ -249,6 +249,38 @@ int cer_plan_prepare(cer_plan* p, const void* fmaps, int fmaps_f16, const void* 
   return CER_OK;
 }
 
+// The plan's own input buffers, for producers that write the kernels' layouts directly (the encoders of
+// csrc/encoder.cu): feature image i (0 = reference image, 1.. = source views) as [px][64] fp16 ALREADY scaled by 1/8,
+// net / inp as [px][64] fp16.  After filling them: cer_plan_prepare_inplace instead of cer_plan_prepare.
+void* cer_plan_feature_buffer(cer_plan* p, int image) {
+  if (!p || !p->cfg.feats_f16 || image < 0 || image > p->cfg.max_views) return nullptr;
+  return (char*)p->feats + (size_t)image * p->px * 64 * 2;
+}
+void* cer_plan_net_buffer(cer_plan* p) { return p ? p->net : nullptr; }
+void* cer_plan_inp_buffer(cer_plan* p) { return p ? p->inp : nullptr; }
+
+int cer_plan_prepare_inplace(cer_plan* p, const float* poses, const float* intrinsics, int n_views, int view_begin,
+                             int view_end, cer_stream_t stream) {
+  CER_REQUIRE(p && poses && intrinsics, "cer_plan_prepare_inplace: null pointer");
+  CER_REQUIRE(p->have_weights, "cer_plan_prepare_inplace: call cer_plan_set_weights first");
+  CER_REQUIRE(p->cfg.feats_f16, "cer_plan_prepare_inplace: needs a plan with fp16 features");
+  CER_REQUIRE(n_views >= 1 && n_views <= p->cfg.max_views, "cer_plan_prepare_inplace: n_views %d outside 1..%d", n_views,
+              p->cfg.max_views);
+  CER_REQUIRE(view_begin >= 0 && view_begin <= view_end && view_end <= n_views, "cer_plan_prepare_inplace: bad view range");
+  cer::g_launches = 0;
+  CER_CUDA(cudaMemsetAsync(p->disp, 0, p->px * 4, (cudaStream_t)stream));   // core/raft.py:52
+  int rc;
+  if (view_end > view_begin &&
+      (rc = cer_projection_matrices(poses, intrinsics, p->ii + view_begin, p->jj + view_begin, view_end - view_begin,
+                                    p->Pij + view_begin * 16, stream)))
+    return rc;
+  p->n_views = n_views;
+  p->vb = view_begin;
+  p->ve = view_end;
+  p->launches = cer::g_launches + 1;
+  return CER_OK;
+}
+
 int cer_plan_build_stage(cer_plan* p, int s, cer_stream_t stream) {
   CER_REQUIRE(p && s >= 0 && s < p->cfg.n_stages, "cer_plan_build_stage: bad stage");
   const int D = p->cfg.D[s];

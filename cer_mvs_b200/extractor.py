@@ -126,13 +126,16 @@ class BasicEncoder(nn.Module):
         self._run(x, out, None, None, scale, normalize)
         return out
 
-    def forward_context(self, x, normalize=False, nchw=False):
+    def forward_context(self, x, normalize=False, nchw=False, out=None):
         """cnet + the split of core/raft.py:58-60: (net = tanh(.), inp = relu(.)), NHWC [n, H/4, W/4, 64] fp16 each
-        (or NCHW [n, 64, H/4, W/4] when ``nchw``)."""
+        (or NCHW [n, 64, H/4, W/4] when ``nchw``); ``out`` = (net, inp) NHWC tensors to fill."""
         if self.norm_fn != "none":
             raise RuntimeError("forward_context is the cnet path")
         H, W = x.shape[-2:]
         n = x.numel() // (3 * H * W)
+        if out is not None:
+            self._run(x, out[0], out[1], None, 1.0, normalize, split=True)
+            return out
         if nchw:
             both = torch.empty(n, 2, 64, H // 4, W // 4, device=x.device, dtype=torch.float16)
             self._run(x, None, None, both, 1.0, normalize, split=True)

@@ -266,6 +266,15 @@ int cer_plan_wait_host(cer_plan* plan);
 int cer_plan_prepare(cer_plan* plan, const void* fmaps, int fmaps_f16, const void* net, const void* inp,
                      int ctx_f16, const float* poses, const float* intrinsics, int n_views,
                      int view_begin, int view_end, cer_stream_t stream);
+/* The plan's own input buffers, for producers that write the kernels' layouts directly (cer_encoder_forward): feature
+ * image i (0 = reference image, 1.. = source views) as [h*w][64] fp16 ALREADY scaled by 1/8 (core/corr.py:30-31), net /
+ * inp as [h*w][64] fp16.  Fill them, then call cer_plan_prepare_inplace (projection matrices, disp = 0) in place of
+ * cer_plan_prepare: no layout kernels run between the encoders and the hot path. */
+void* cer_plan_feature_buffer(cer_plan* plan, int image);
+void* cer_plan_net_buffer(cer_plan* plan);
+void* cer_plan_inp_buffer(cer_plan* plan);
+int cer_plan_prepare_inplace(cer_plan* plan, const float* poses, const float* intrinsics, int n_views, int view_begin,
+                             int view_end, cer_stream_t stream);
 int cer_plan_build_stage(cer_plan* plan, int stage, cer_stream_t stream);
 /* Sharded build: units [unit_begin, unit_end) of the stage's n_views * D (view, hypothesis) units, view-major, into a
  * zeroed partial volume (cer_plan_partial_volume); the views they touch must have been prepared.  An empty range only

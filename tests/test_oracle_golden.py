@@ -149,3 +149,16 @@ def test_fusion_oracle_matches_reference_functions(golden, case):
     assert (keep != g[f"{case}_geo_mask"]).mean() < 3e-3
     np.testing.assert_allclose(depth_est[same], g[f"{case}_depth_est"][same], rtol=2e-6)
     assert 0.3 < g[f"{case}_geo_mask"].mean() < 0.95
+
+
+@pytest.mark.parametrize("kind", ["fnet", "cnet"])
+def test_encoder_oracle_matches_reference_module(golden, kind):
+    """oracle/cer_oracle.basic_encoder against the reference's own BasicEncoder (core/extractor.py, fp32 CPU run)."""
+    g = golden("ops_encoder")
+    dim = 64 if kind == "fnet" else 128
+    sd = O.to_torch_sd(synth.make_encoder_weights(seed=int(g[f"{kind}_seed"]), out_dim=dim))
+    x = t(synth.make_image(72, 104, n=1, seed=int(g["image_seed"]))) * (2 / 255.) - 1
+    out = O.basic_encoder(sd, x, kind == "fnet", autocast=False).numpy()
+    np.testing.assert_allclose(out, g[f"{kind}_out"], rtol=1e-4, atol=1e-4)
+    net, inp = O.context_split(t(g["cnet_out"]))
+    assert float(net.abs().max()) <= 1.0 and float(inp.min()) >= 0.0
