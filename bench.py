@@ -481,6 +481,51 @@ def run_ours(args):
         rms = timed(lambda: hp(*scene.dev_args()), args.steps, 3) / args.steps
         sharded = {"replicas_depth_maps_per_s": world * 1e3 / rms, "replicas_ms_per_depth_map": rms}
 
+    # ---- whole RAFT.forward: images in -> encoders (csrc/encoder.cu) -> hot path, all on our kernels ----
+    whole = None
+    if rank == 0 and world == 1 and cfg == "cfg2" and not args.no_whole_forward:
+        from cer_mvs_b200.raft import RAFT
+        sdw = {}
+        for k, v in synth.make_encoder_weights(seed=0, out_dim=64).items():
+            sdw["fnet." + k] = torch.from_numpy(v)
+        for k, v in synth.make_encoder_weights(seed=1, out_dim=128).items():
+            sdw["cnet." + k] = torch.from_numpy(v)
+        for k, v in sd.items():
+            sdw["update_block." + k] = torch.from_numpy(v)
+        model = RAFT(cascade=CASCADE, test_mode=True)
+        model.load_state_dict(sdw, strict=True)
+        model = model.to(dev).eval()
+        h_images = torch.from_numpy(synth.make_image(Hc, Wc, n=Vc + 1, seed=0))[None].pin_memory()
+        d_images = h_images.to(dev)
+        with torch.no_grad():
+            wms = timed(lambda: model(d_images, scene.d_poses, scene.d_K, scale=1.0), max(args.steps // 2, 3), 3)
+            wms /= max(args.steps // 2, 3)
+        whole = {"what": "cer_mvs_b200.raft.RAFT.forward: fp32 images in (0..255), normalisation + fnet x%d + cnet "
+                         "(hand-written mma.sync convs, instance norm) + hot path, images resident" % (Vc + 1),
+                 "ms_per_depth_map": wms, "depth_maps_per_s": 1e3 / wms,
+                 "encoder_gflop_per_depth_map": 71.0 * (Vc + 2)}
+        if not args.no_reference_gpu:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            try:
+                import refrun
+                if refrun.available("gpu"):
+                    ref = refrun.import_reference("gpu")
+                    refrun.restore_reference_classes()
+                    rmodel = ref.raft.RAFT(cascade=CASCADE, test_mode=True)
+                    rmodel.load_state_dict(sdw, strict=True)
+                    rmodel = rmodel.to(dev).eval()
+                    sc64 = torch.tensor([1.0], dtype=torch.float64, device=dev)
+                    with torch.no_grad():
+                        rms = timed(lambda: rmodel(d_images.clone(), scene.d_poses.clone(), scene.d_K.clone(), scale=sc64),
+                                    2, 1) / 2
+                    whole["reference_ms_per_depth_map"] = rms
+                    whole["speedup_vs_reference_gpu"] = rms / wms
+                    del rmodel
+            except Exception as e:  # noqa: BLE001
+                whole["reference_unavailable"] = repr(e)[:200]
+        del model, d_images
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and cfg == "cfg2":
         # one bounded sample of ~10-20 s of CPU work: 24 of 296 rows, 1+1 iterations
@@ -531,7 +576,7 @@ def run_ours(args):
                     "ms_per_step": 1e3 * e2e_s / args.steps, "sync_call_ms": sync_ms, "api": e2e_api},
             "gpu_launches": launches,
             "clocks": clk, "roofline": roof, "build_roofline": build_roof, "lookup_roofline": lookup_roof,
-            "cpu_baseline": cpu, "reference_gpu": ref_gpu, "kernels": kernels,
+            "cpu_baseline": cpu, "reference_gpu": ref_gpu, "whole_forward": whole, "kernels": kernels,
         }
         if ms8:
             line["iters_8_8"] = {"value": world * 1e3 / ms8, "unit": "depth-maps/s", "ms_per_step": ms8,
@@ -552,6 +597,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=8, help="rows of the 296-row grid in one CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-this-GPU leg")
+    ap.add_argument("--no-whole-forward", action="store_true", help="skip the whole-RAFT.forward leg (encoders + hot path)")
     ap.add_argument("--profile-step", action="store_true", help="ncu helper: warm-up + one eager step only")
     ap.add_argument("--conv-variant", type=int, default=None, help="cer_set_conv_variant (A/B experiments)")
     ap.add_argument("--build-variant", type=int, default=None, help="cer_set_build_variant (A/B experiments)")

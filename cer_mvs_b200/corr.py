@@ -9,19 +9,29 @@ Differences a caller can see (both allowed by the reference's own consumer, core
   Pass ``per_view=True`` (or set ``CorrBlock.per_view_default``) for the reference's exact layout.
 * ``corr_pyramid`` is materialised lazily (the lookup kernel rebuilds levels 1..L-1 on the fly).
 """
+import weakref
+
 import torch
 
 from . import _lib
 
-_feat_cache = {}
+_feat_cache = {}       # id(fmaps) -> (weakref(fmaps), key, NHWC copy); an entry dies with the caller's tensor
+
+
+def clear_feature_cache():
+    """Drop every cached NHWC feature copy (call before ``torch.cuda.empty_cache()`` to return the memory)."""
+    _feat_cache.clear()
 
 
 def _prepare_features(fmaps: torch.Tensor):
     """[1,n,64,h,w] (fp16|fp32) -> NHWC [n,h,w,64] scaled by 1/8 (core/corr.py:29-35), cached for the
-    second cascade stage (the reference redoes this per view per stage)."""
+    second cascade stage (the reference redoes this per view per stage).  The cache holds only a weak
+    reference to ``fmaps``: when the caller drops the feature maps (end of ``RAFT.forward``) the NHWC copy
+    goes with them, so peak memory follows the reference's (inference.py empties the allocator cache per image)."""
     key = (fmaps.data_ptr(), fmaps._version, tuple(fmaps.shape), fmaps.dtype, fmaps.device)
-    hit = _feat_cache.get("k")
-    if hit is not None and hit[0] == key:
+    ident = id(fmaps)
+    hit = _feat_cache.get(ident)
+    if hit is not None and hit[0]() is fmaps and hit[1] == key:
         return hit[2]
     B, n, C, h, w = fmaps.shape
     f16 = fmaps.dtype == torch.float16
@@ -29,7 +39,7 @@ def _prepare_features(fmaps: torch.Tensor):
     dst = torch.empty(n, h, w, C, device=fmaps.device, dtype=torch.float16 if f16 else torch.float32)
     _lib.check(_lib.lib().cer_nchw_to_nhwc(src.data_ptr(), int(f16), dst.data_ptr(), int(f16), n, C, h, w, 0.125,
                                            _lib.stream_ptr()), "feature layout")
-    _feat_cache["k"] = (key, fmaps, dst)      # keeps `fmaps` alive so the pointer cannot be recycled
+    _feat_cache[ident] = (weakref.ref(fmaps, lambda _r, ident=ident: _feat_cache.pop(ident, None)), key, dst)
     return dst
 
 

@@ -1,5 +1,8 @@
 """Image preparation, depth output and the multi-resolution merge around the hot path,
-under the reference's own function names so that ``inference.py`` / ``multires.py`` can call them unchanged:
+under the reference's own function names and argument meaning.  These are DEVICE-side equivalents: the reference
+calls ``scale_operation`` / ``crop_operation`` on CPU tensors before ``.cuda()`` (inference.py:45-50) and
+``multires`` works on numpy arrays, so a caller moves the images to the GPU first (``images.cuda()``), then calls
+these; ``install.install()`` does not substitute them.  CPU tensors raise -- there is no CPU path.
 
 * ``scale_operation`` / ``crop_operation``  (utils/data_utils.py:58-79)
 * ``normalize_images``                       (core/raft.py:40-41, ``images *= 2 / 255.; images -= 1``)
