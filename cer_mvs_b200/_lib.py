@@ -49,6 +49,7 @@ SIGNATURES = {
     "cer_encoder_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_float, c_void_p]),
     "cer_set_conv_variant": (c_int, [c_int]),
+    "cer_lookup_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
     "cer_set_lookup_variant": (c_int, [c_int]),
     "cer_debug_set_conv_profile": (c_int, [c_void_p]),
     "cer_gru_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),

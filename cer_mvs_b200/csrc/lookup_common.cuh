@@ -149,82 +149,4 @@ __device__ __forceinline__ void pyr_taps33(const float* L0, const float* L1, con
   }
 }
 
-// ---- level-0-only staging (lookup_enc1_v3_kernel): 9.3 KB per warp instead of 15.5 KB ------------------------------
-// Row = [4 zeros | D level-0 values | 4+ zeros], pitch 73 floats (odd).  Levels 1 and 2 are pooled on the fly with the
-// same expressions as pyr_value; the zero pads make every pooled value just outside a level exactly 0, which is the
-// grid_sample zero padding, so the taps stay unconditional loads.
-constexpr int kPyr0Pitch = 73;
-constexpr int kPyr0WarpFloats = 32 * kPyr0Pitch;
-
-template <int D>
-__device__ __forceinline__ void pyr0_store_chunk(const float4 (&rv)[D / 4], float* L0, int lane) {
-  static_assert(D % 4 == 0 && D + 8 <= kPyr0Pitch, "pitch is sized for D <= 64");
-  constexpr int NV = D / 4;
-  {
-    float* r0 = L0 + lane * kPyr0Pitch;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      r0[k] = 0.f;
-      r0[4 + D + k] = 0.f;
-    }
-  }
-  const int rot = lane >> 3;
-#pragma unroll
-  for (int it = 0; it < NV; ++it) {
-    const int f = it * 32 + lane;
-    const int pp = f / NV, i = (f % NV) * 4;
-    const float4 v = rv[it];
-    float* d0 = L0 + pp * kPyr0Pitch + 4 + i;
-    const float a0 = (rot & 1) ? v.y : v.x, a1 = (rot & 1) ? v.z : v.y, a2 = (rot & 1) ? v.w : v.z, a3 = (rot & 1) ? v.x : v.w;
-    const float c0 = (rot & 2) ? a2 : a0, c1 = (rot & 2) ? a3 : a1, c2 = (rot & 2) ? a0 : a2, c3 = (rot & 2) ? a1 : a3;
-    d0[(0 + rot) & 3] = c0;
-    d0[(1 + rot) & 3] = c1;
-    d0[(2 + rot) & 3] = c2;
-    d0[(3 + rot) & 3] = c3;
-  }
-}
-
-// one tap of level LVL read from the zero-padded level-0 row (lrow = first level-0 value)
-template <int LVL>
-__device__ __forceinline__ float lookup_tap_l0(const float* lrow, const LevelConst k, float cl, int j) {
-  const float x0 = __fadd_rn((float)j, cl);
-  const float q0 = __fmul_rn(x0, k.rcp);
-  const float q = __fmaf_rn(__fmaf_rn(-q0, k.wm1, x0), k.rcp, q0);
-  const float xn = __fmaf_rn(2.f, q, -1.f);
-  const float xp = __fmul_rn(__fadd_rn(xn, 1.f), k.hw);
-  const float fl = floorf(xp);
-  const float w1 = xp - fl;
-  const float w0 = (fl + 1.f) - xp;
-  const bool inr = fl >= -1.f && fl < k.fW;
-  const int i0 = inr ? (int)fl : -1;
-  float v0, v1;
-  if (LVL == 0) {
-    v0 = lrow[i0];
-    v1 = lrow[i0 + 1];
-  } else if (LVL == 1) {
-    const float* p = lrow + 2 * i0;
-    v0 = (p[0] + p[1]) * 0.5f;
-    v1 = (p[2] + p[3]) * 0.5f;
-  } else {
-    const float* p = lrow + 4 * i0;
-    v0 = ((p[0] + p[1]) * 0.5f + (p[2] + p[3]) * 0.5f) * 0.5f;
-    v1 = ((p[4] + p[5]) * 0.5f + (p[6] + p[7]) * 0.5f) * 0.5f;
-  }
-  const float v = v0 * w0 + v1 * w1;
-  return inr ? v : 0.f;
-}
-
-template <int D>
-__device__ __forceinline__ void pyr0_taps33(const float* L0, int lane, float c, float (&tp)[33]) {
-  const float* r0 = L0 + lane * kPyr0Pitch + 4;
-  constexpr LevelConst k0 = level_const(D, 0), k1 = level_const(D, 1), k2 = level_const(D, 2);
-  const float c1 = c * 0.5f, c2 = c * 0.25f;
-#pragma unroll
-  for (int j = 0; j < 11; ++j) {
-    tp[j] = lookup_tap_l0<0>(r0, k0, c, j - 5);
-    tp[11 + j] = lookup_tap_l0<1>(r0, k1, c1, j - 5);
-    tp[22 + j] = lookup_tap_l0<2>(r0, k2, c2, j - 5);
-  }
-}
-
 }  // namespace cer

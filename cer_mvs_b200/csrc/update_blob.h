@@ -37,6 +37,7 @@ struct BlobLayout {
   // the output channels is one contiguous bulk copy
   size_t p_wg;     // [4*9] tiles, N = 192
   size_t p_wd0[2]; // [1*9] tiles, N = 256
+  size_t w1f;      // u32 [3][32][8][2]  corr_encoder.0 as mma.sync m16n8k16 B fragments (lookup_enc1_v4_kernel)
   size_t total;
 };
 
@@ -65,6 +66,7 @@ inline BlobLayout blob_layout() {
   for (int s = 0; s < 2; ++s) L.t_wd0[s] = take(9 * 64 * kDelta0 * 2);
   L.p_wg = take(4 * 9 * 64 * kGateN * 2);
   for (int s = 0; s < 2; ++s) L.p_wd0[s] = take(9 * 64 * kDelta0 * 2);
+  L.w1f = take((kCorrK / 16) * 32 * 8 * 2 * 4);
   L.total = o;
   return L;
 }

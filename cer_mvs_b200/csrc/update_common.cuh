@@ -27,7 +27,7 @@ struct ConvArgs {
   __half* rnet;        // EPI_GATES: write
   float* qx;           // EPI_GATES: write; EPI_GRUOUT: read
   const float* w2;     // EPI_DELTA: [9][256]
-  float* s9;           // EPI_DELTA: [px][2][9] partial dots of the second delta conv
+  float* s9;           // EPI_DELTA: [2][9][px] partial dots of the second delta conv (s9_index)
   unsigned long long* prof;   // optional (tools/conv_roles.py): per-role wait/work cycle counters of CTA 0, else null
   // Tile-level dependencies between consecutive tcgen05 convs of one iteration (same 16 x 8 tiling).  flags_out: this
   // launch sets flags_out[tile] = 1 once every store of the tile is visible.  flags_in: instead of waiting for the whole
@@ -36,6 +36,12 @@ struct ConvArgs {
   int* flags_out;
   const int* flags_in;
 };
+
+// Partial dots of the second delta conv: plane-major [part 2][tap 9][px], so that the consumer's nine neighbour reads
+// per pixel are nine coalesced row reads per warp (the pixel-major layout of round 1 cost 18 sector-scattered loads).
+__host__ __device__ __forceinline__ long long s9_index(long long px, int part, int t, long long p) {
+  return (long long)(part * 9 + t) * px + p;
+}
 
 constexpr int kFlagIters = 64;      // iterations per stage with tile flags (later ones fall back to grid dependencies)
 constexpr int kFlagKernels = 3;     // corr-encoder 3x3, gates, q/GRU publish; gates, q/GRU, delta consume
@@ -60,7 +66,7 @@ inline UpdateWs carve_ws(void* base, int h, int wd) {
   w.z = (__half*)take(px * 64 * 2);
   w.rnet = (__half*)take(px * 64 * 2);
   w.qx = (float*)take(px * 64 * 4);
-  w.s9 = (float*)take(px * 18 * 4);   // [px][2 column halves][9 taps] (the mma.sync path fills half 0 only)
+  w.s9 = (float*)take(px * 18 * 4);   // [2 column halves][9 taps][px] (the mma.sync path fills half 0 only)
   w.flags_bytes = (size_t)kFlagIters * kFlagKernels * flag_tiles(h, wd) * sizeof(int);
   w.flags = (int*)take(w.flags_bytes);
   w.total = o;

@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(256) lookup_enc1_kernel(
         for (int t = 0; t < 9; ++t) {
           const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
           if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-            const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
-            s += (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
+            const float* q = s9 + s9_index(px, 0, t, (long long)yy * w + xx);
+            s += (parts == 2) ? __ldg(q) + __ldg(q + 9 * (long long)px) : __ldg(q);
           }
         }
         dsp += h_round(0.01f * h_round(s + __ldg(bd1)));
@@ -256,121 +256,198 @@ static size_t lookup_enc1_smem(int D) {
 }
 
 // ------------------------------------------------------------------------------------------
-// KA v2 (plan, D = 64 / 44): the same fused step, restructured around what bounded v1 (ncu: issue slots 37 %, warps
-// stalled on block barriers and on the dependent load -> tap -> MMA phases, 800 instructions per warp):
-//   * warp-autonomous: each warp owns 32 consecutive pixels (8 KB of contiguous volume rows) end to end; the only
-//     block barrier is the one that publishes the shared 1x1 weights, right before the MMA.  Warps of a CTA and CTAs
-//     of an SM drift into different phases, so row loads of one overlap the tap arithmetic of another.
-//   * every load of the chunk (16 x 16-byte row loads per lane, disparity, origin, 18 delta partials) is issued
-//     before the first use: one latency exposure per chunk instead of three.
-//   * the pyramid is materialised once per chunk in shared memory, zero padded on both sides (levels 1-2 straight
-//     from the row registers), so a tap is two unconditional loads; lane = pixel, odd row pitches.
-//   * the per-tap IEEE division is three FMAs (lookup_tap_padded), bit-identical to v1.
-//   * e1 leaves through a shared-memory transpose: 512-byte contiguous stores instead of 16-byte fragments.
+// KA v4 (plan, D = 64 / 44): the same fused step as one wave of warp-autonomous chunks.
+//   * a warp owns 32 consecutive pixels end to end and the kernel has NO block barrier: 5 warps per CTA, 5 CTAs per SM
+//     = 25 resident warps per SM = 3 700 chunks at cfg 2 = exactly one wave on 148 SMs (round 1: 1.25 waves of 4-warp CTAs).
+//   * the level-0 volume rows go global -> shared memory by cp.async (no row registers, no store instructions); row
+//     pitch = 4 (mod 32) words or 12, so a 16-byte load per lane at equal offsets is conflict-free.
+//   * ONE shared window per pixel: the 12 aligned 16-byte pieces [f2-5, f2+6] around the level-2 centre hold every value
+//     the 33 taps touch (the level-1 and level-0 windows are nested in it).  Pieces outside the row come from one zero
+//     piece (= grid_sample's zero padding, exact because D % 4 == 0).  Pair sums S and quad sums Q of the pieces are the
+//     pooled levels (same expressions as pyr_value up to the exact power-of-two scalings, folded into the weights).
+//   * per level the centre coordinate runs through the reference's normalise / unnormalise round trip exactly
+//     (bilinear_sampler.py:12 + grid_sample); the ten other taps of the level reuse its floor and weights.  The reference
+//     recomputes the round trip per tap, which moves a tap position by <= 1 ulp of the coordinate (4e-6 at 64): the taps
+//     differ from the general kernel by <= 5e-6 * |v1 - v0| before they are rounded to fp16 (autocast) -- 12 loads and
+//     ~220 instructions per pixel instead of 154 loads and ~1 000.
+//   * the 1x1 weights are read as ready-made mma.sync B fragments (BlobLayout::w1f, 6 KB, L1-resident: every other
+//     global read of the kernel bypasses L1): no weight tile in shared memory.  The bias rides in the K padding (plane
+//     33 = 1, fragment row 33 = bias), so the epilogue is round + max.  The 18 delta partials are 18 coalesced row reads (plane-major s9).
 // ------------------------------------------------------------------------------------------
-constexpr int kL2_WARPS = 4;
-constexpr int kL2_P0 = kPyrP0, kL2_P1 = kPyrP1, kL2_P2 = kPyrP2;      // padded level rows (lookup_common.cuh)
-constexpr int kL2_WARP_FLOATS = kPyrWarpFloats;
-constexpr int kL2_OUT_PITCH = 144;                           // bytes per pixel of the e1 staging tile
-
-static_assert(32 * kA1Pitch * 2 + 32 * kL2_OUT_PITCH <= kPyr0WarpFloats * 4, "A tile + e1 staging tile alias the level-0 rows");
+constexpr int kL4_WARPS = 5;
+constexpr int kL4_OUT_PITCH = 144;                            // bytes per pixel of the e1 staging tile
+constexpr int kL4_TILE_BYTES = 32 * kA1Pitch * 2 + 32 * kL4_OUT_PITCH;   // A tile + e1 staging tile (alias the rows)
 template <int D>
-__global__ void __launch_bounds__(kL2_WARPS * 32, 5) lookup_enc1_v3_kernel(
+struct L4 {
+  static constexpr int NV = D / 4;                             // 16-byte pieces per row
+  static constexpr int PITCH = (D % 32 == 0) ? D + 4 : D;      // floats
+  static constexpr int ROW_BYTES = 32 * PITCH * 4;
+  static constexpr int ZERO_OFF = ROW_BYTES > kL4_TILE_BYTES ? ROW_BYTES : kL4_TILE_BYTES;
+  static constexpr int WARP_BYTES = ZERO_OFF + 16;
+  static_assert(D % 4 == 0 && D >= 8 && D <= 64, "16-byte row pieces; one window covers a level-2 row of <= 16 values");
+  static_assert(PITCH % 4 == 0 && (PITCH % 32) % 8 == 4, "pitch = 4, 12, 20 or 28 (mod 32) words");
+};
+
+__device__ __forceinline__ void lds128(float (&r)[48], int i, uint32_t addr) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(r[i]), "=f"(r[i + 1]), "=f"(r[i + 2]), "=f"(r[i + 3]) : "r"(addr));
+}
+
+// streaming read that leaves L1 to the 6 KB of weight fragments every warp of the SM re-reads
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// centre tap (offset 0) of one level: x0 = cl -> 2*x0/(W-1) - 1 -> ((xn + 1) / 2) * (W-1), rounded like the reference
+__device__ __forceinline__ float lookup_centre(const LevelConst k, float cl) {
+  const float q0 = __fmul_rn(cl, k.rcp);
+  const float q = __fmaf_rn(__fmaf_rn(-q0, k.wm1, cl), k.rcp, q0);
+  const float xn = __fmaf_rn(2.f, q, -1.f);
+  return __fmul_rn(__fadd_rn(xn, 1.f), k.hw);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kL4_WARPS * 32, 5) lookup_enc1_v4_kernel(
     const float* __restrict__ volume, const float* __restrict__ origin, float* __restrict__ disp,
     const float* __restrict__ s9, int parts, const float* __restrict__ bd1, int apply_prev, float incre,
-    const __half* __restrict__ w1, const float* __restrict__ b1, __half* __restrict__ e1, int h, int w) {
-  static_assert(D % 4 == 0 && D <= 64 && D >= 8, "row registers / pitches are sized for D <= 64, 16-byte row pieces");
-  constexpr int NV = D / 4;                                  // 16-byte pieces per pixel row = row loads per lane
+    const uint4* __restrict__ w1f, __half* __restrict__ e1, int h, int w) {
+  using C = L4<D>;
+  constexpr int NV = C::NV, P = C::PITCH;
   extern __shared__ __align__(16) unsigned char fsm[];
-  __half* sW = reinterpret_cast<__half*>(fsm);                                   // [48][kW1Pitch]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* L0 = reinterpret_cast<float*>(fsm + kCorrK * kW1Pitch * 2) + warp * kPyr0WarpFloats;
+  unsigned char* wbase = fsm + warp * C::WARP_BYTES;
   const int px = h * w;
-  // a warp past the end of the image (last CTA only) runs on pixel 0 with npix = 0: every store is guarded by npix, and
-  // the CTA keeps one barrier for all warps
-  const int p0_raw = (blockIdx.x * kL2_WARPS + warp) * 32;
-  const int p0 = p0_raw < px ? p0_raw : 0;
+  const int p0 = (blockIdx.x * kL4_WARPS + warp) * 32;
   pdl_trigger();
-  // 1x1 weights: constants, requested before the dependency wait; they are parked in registers until the chunk's own
-  // loads are in flight too, so a CTA pays ONE global-latency exposure, not two (ncu: 20 % of the v2 kernel's stall
-  // samples sat on the weight store that used to come first)
-  constexpr int WQ = kCorrK * kHid / 8 / (kL2_WARPS * 32);
-  static_assert(WQ * kL2_WARPS * 32 * 8 == kCorrK * kHid, "weight pieces divide evenly over the CTA");
-  uint4 wreg[WQ];
-#pragma unroll
-  for (int q = 0; q < WQ; ++q) wreg[q] = __ldg(reinterpret_cast<const uint4*>(w1) + q * kL2_WARPS * 32 + tid);
-  pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
-  const int npix = p0_raw < px ? min(32, px - p0) : 0;
+  if (p0 >= px) return;                 // no block barrier in this kernel: a surplus warp of the last CTA just leaves
+  const int npix = min(32, px - p0);
   const bool live = lane < npix;
   const int p = p0 + (live ? lane : 0);
+  const uint32_t rows_s = smem_u32(wbase), zero_s = rows_s + C::ZERO_OFF;
+  if (lane == 0) *reinterpret_cast<float4*>(wbase + C::ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
 
-  // ---- issue every load of the chunk ----
-  float4 rv[NV];
-  pyr_load_chunk<D>(volume + (long long)p0 * D, npix, lane, rv);
-  float dsp = disp[p];
-  const float org = __ldg(origin + p);
-  float sv[9];
+  // ---- the chunk's rows: 32 * D contiguous floats, piece f = it * 32 + lane (coalesced) -> row f / NV ----
+  {
+    const float4* vsrc = reinterpret_cast<const float4*>(volume + (long long)p0 * D);
+    const int nvec = npix * NV;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int f = it * 32 + lane;
+      if (f < nvec) cp_async16(rows_s + ((f / NV) * P + (f % NV) * 4) * 4, vsrc + f, true);
+    }
+    cp_async_commit();
+  }
+  float dsp = ldg_stream(disp + p);     // (written below by this thread only)
+  const float org = ldg_stream(origin + p);
   if (apply_prev) {     // K6 of the previous iteration: delta = fp16(0.01 * fp16(b + sum_t s9[p + off_t][t]))
+    // all 18 partials are requested before the first use: the addresses of neighbours outside the image are clamped
+    // to the pixel itself (a legal address) and the value is dropped, so no load sits behind a branch
     const int x = p % w, y = p / w;
+    const bool oky[3] = {y > 0, true, y < h - 1}, okx[3] = {x > 0, true, x < w - 1};
+    float sa[9], sb[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      sv[t] = 0.f;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-        const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
-        sv[t] = (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
-      }
+      const bool ok = oky[t / 3] && okx[t % 3];
+      const float* q = s9 + (long long)t * px + (ok ? p + (t / 3 - 1) * w + (t % 3 - 1) : p);     // s9_index(px, 0, t, .)
+      sa[t] = ldg_stream(q);
+      sb[t] = (parts == 2) ? ldg_stream(q + 9 * (long long)px) : 0.f;
     }
-  }
-
-#pragma unroll
-  for (int q = 0; q < WQ; ++q) {
-    const int i = q * kL2_WARPS * 32 + tid;
-    *reinterpret_cast<uint4*>(sW + (i / (kHid / 8)) * kW1Pitch + (i % (kHid / 8)) * 8) = wreg[q];
-  }
-  // ---- pyramid rows -> shared memory ----
-  pyr0_store_chunk<D>(rv, L0, lane);
-  if (apply_prev) {
     float s = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int x = p % w, y = p / w;
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) s += sv[t];
+      const float sv = (parts == 2) ? sa[t] + sb[t] : sa[t];
+      if (oky[t / 3] && okx[t % 3]) s += sv;
     }
     dsp += h_round(0.01f * h_round(s + __ldg(bd1)));
     if (live) disp[p] = dsp;
   }
-  const float c = live ? lookup_coord(dsp, org, incre, D) : 0.f;
+  // coordinates past the window are all "every tap outside": cap them so that the integer arithmetic below is safe.
+  // A lane without a pixel (last chunk) takes the cap: all of its pieces are the zero piece, its A row is zero.
+  const float c = live ? fminf(lookup_coord(dsp, org, incre, D), 4096.f) : 4096.f;
+
+  constexpr LevelConst k0 = level_const(D, 0), k1 = level_const(D, 1), k2 = level_const(D, 2);
+  const float xp0 = lookup_centre(k0, c), xp1 = lookup_centre(k1, c * 0.5f), xp2 = lookup_centre(k2, c * 0.25f);
+  const int f2 = (int)floorf(xp2);
+  // nest the level-1 / level-0 floors in the level-2 window; a floor that rounding put one step outside moves back and
+  // the weights (computed from the moved floor) extrapolate by that ulp, which is the same value by continuity
+  const int f1 = min(max((int)floorf(xp1), 2 * f2), 2 * f2 + 1);
+  const int f0 = min(max((int)floorf(xp0), 4 * f2), 4 * f2 + 3);
+  const float w21 = (xp2 - (float)f2) * 0.25f, w20 = (((float)f2 + 1.f) - xp2) * 0.25f;     // * 1/4: level-2 pooling
+  const float w11 = (xp1 - (float)f1) * 0.5f, w10 = (((float)f1 + 1.f) - xp1) * 0.5f;       // * 1/2: level-1 pooling
+  const float w01 = xp0 - (float)f0, w00 = ((float)f0 + 1.f) - xp0;
+  const int o1 = f1 - 2 * f2, o0 = f0 - 4 * f2;
+
+  cp_async_wait<0>();
   __syncwarp();
 
   // ---- 33 taps of this lane's pixel -> fp16 A row (registers) ----
   uint32_t arow[kCorrK / 2];
   {
-    float tp33[33], tp[kCorrK];
-    pyr0_taps33<D>(L0, lane, c, tp33);
+    float R[48];
+    const uint32_t row_s = rows_s + lane * (P * 4);
 #pragma unroll
-    for (int k = 0; k < kCorrPlanes; ++k) tp[k] = tp33[k];
+    for (int n = 0; n < 12; ++n) {
+      const int pi = f2 - 5 + n;
+      lds128(R, 4 * n, (unsigned)pi < (unsigned)NV ? row_s + pi * 16 : zero_s);
+    }
+    auto pack = [&](float lo, float hi) {
+      const __half2 hh = __floats2half2_rn(lo, hi);
+      return *reinterpret_cast<const uint32_t*>(&hh);
+    };
 #pragma unroll
-    for (int k = kCorrPlanes; k < kCorrK; ++k) tp[k] = 0.f;
+    for (int k = 17; k < kCorrK / 2; ++k) arow[k] = 0u;        // planes 34..47: K padding
+    float S[24];
 #pragma unroll
-    for (int k = 0; k < kCorrK / 2; ++k) {
-      const __half2 hh = __floats2half2_rn(live ? tp[2 * k] : 0.f, live ? tp[2 * k + 1] : 0.f);
-      arow[k] = *reinterpret_cast<const uint32_t*>(&hh);
+    for (int m = 0; m < 24; ++m) S[m] = __fadd_rn(R[2 * m], R[2 * m + 1]);
+    float t11;                                                  // plane 11 pairs with plane 10 of level 0
+    {   // level 2 (planes 22..32): value k2 = f2 - 5 + n is quad sum n
+      float Q[12], t[11];
+#pragma unroll
+      for (int n = 0; n < 12; ++n) Q[n] = __fadd_rn(S[2 * n], S[2 * n + 1]);
+#pragma unroll
+      for (int j = 0; j < 11; ++j) t[j] = __fmaf_rn(Q[j + 1], w21, __fmul_rn(Q[j], w20));
+#pragma unroll
+      for (int k = 0; k < 5; ++k) arow[11 + k] = pack(t[2 * k], t[2 * k + 1]);
+      arow[16] = pack(t[10], 1.f);                              // plane 33 = 1: row 33 of the fragments is the bias
+    }
+    {   // level 1 (planes 11..21): value k1 = f1 - 5 + i is pair sum 5 + o1 + i
+      float V[12], t[11];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) V[i] = o1 ? S[6 + i] : S[5 + i];
+#pragma unroll
+      for (int j = 0; j < 11; ++j) t[j] = __fmaf_rn(V[j + 1], w11, __fmul_rn(V[j], w10));
+      t11 = t[0];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) arow[6 + k] = pack(t[1 + 2 * k], t[2 + 2 * k]);
+    }
+    {   // level 0 (planes 0..10): value k0 = f0 - 5 + i is window element 15 + o0 + i
+      float T[14], t[11];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) T[i] = (o0 & 1) ? R[16 + i] : R[15 + i];
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const float v0 = (o0 & 2) ? T[j + 2] : T[j], v1 = (o0 & 2) ? T[j + 3] : T[j + 1];
+        t[j] = __fmaf_rn(v1, w01, __fmul_rn(v0, w00));
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) arow[k] = pack(t[2 * k], t[2 * k + 1]);
+      arow[5] = pack(t[10], t11);
     }
   }
-  __syncwarp();                       // every lane is done with the pyramid rows: the A tile may overwrite level 0
-  __half* sA = reinterpret_cast<__half*>(L0);
+  __syncwarp();                       // every lane is done with its row: the A tile may overwrite the rows
+  __half* sA = reinterpret_cast<__half*>(wbase);
 #pragma unroll
   for (int k = 0; k < kCorrK / 8; ++k)
     *reinterpret_cast<uint4*>(sA + lane * kA1Pitch + k * 8) =
         make_uint4(arow[4 * k], arow[4 * k + 1], arow[4 * k + 2], arow[4 * k + 3]);
-  __syncthreads();                    // the only CTA barrier: the 1x1 weights of all four warps are in place (and my A tile)
+  __syncwarp();
 
   // ---- 1x1 conv on mma.sync (two 16-pixel tiles), bias, fp16 rounding, ReLU -> staging tile ----
-  unsigned char* sO = reinterpret_cast<unsigned char*>(L0) + 32 * kA1Pitch * 2;     // behind the A tile
-  const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * kW1Pitch + 8 * (lane >> 4)) * 2;
+  unsigned char* sO = wbase + 32 * kA1Pitch * 2;     // behind the A tile
   const int g = lane >> 2, q = lane & 3;
+  const __half2 hzero = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     float acc[8][4];
@@ -380,28 +457,23 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 5) lookup_enc1_v3_kernel(
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
     const uint32_t aBase = smem_u32(sA) + ((mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kA1Pitch + 8 * (lane >> 4)) * 2;
 #pragma unroll
-    for (int k16 = 0; k16 < kCorrK / 16; ++k16) {
+    for (int kb = 0; kb < kCorrK / 16; ++kb) {
       uint32_t a[4];
-      ldmatrix_x4(a, aBase + k16 * 32);
+      ldmatrix_x4(a, aBase + kb * 32);
+      const uint4* wf = w1f + (kb * 32 + lane) * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t b[4];
-        ldmatrix_x4_trans(b, bBase + (k16 * 16 * kW1Pitch + j * 16) * 2);
-        mma16816(acc[2 * j], a, b[0], b[1]);
-        mma16816(acc[2 * j + 1], a, b[2], b[3]);
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint4 b = __ldg(wf + jj);          // n-blocks 2jj, 2jj+1: (b0, b1) each
+        mma16816(acc[2 * jj], a, b.x, b.y);
+        mma16816(acc[2 * jj + 1], a, b.z, b.w);
       }
     }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int row = mt * 16 + g + 8 * half;
+    for (int j = 0; j < 8; ++j)         // relu(fp16(acc)) == fp16 max(., 0) of the rounded sum; the bias came in through K
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = j * 8 + q * 2;
-        const float v0 = fmaxf(h_round(acc[j][2 * half] + __ldg(b1 + n)), 0.f);
-        const float v1 = fmaxf(h_round(acc[j][2 * half + 1] + __ldg(b1 + n + 1)), 0.f);
-        *reinterpret_cast<__half2*>(sO + row * kL2_OUT_PITCH + n * 2) = __floats2half2_rn(v0, v1);
-      }
-    }
+      for (int half = 0; half < 2; ++half)
+        *reinterpret_cast<__half2*>(sO + (mt * 16 + g + 8 * half) * kL4_OUT_PITCH + (j * 8 + q * 2) * 2) =
+            __hmax2(__floats2half2_rn(acc[j][2 * half], acc[j][2 * half + 1]), hzero);
   }
   __syncwarp();
   // ---- e1: 4 pixels (512 contiguous bytes) per warp store ----
@@ -410,11 +482,12 @@ __global__ void __launch_bounds__(kL2_WARPS * 32, 5) lookup_enc1_v3_kernel(
     const int row = it * 4 + (lane >> 3), cchunk = lane & 7;
     if (row < npix)
       *reinterpret_cast<uint4*>(e1 + (long long)(p0 + row) * 64 + cchunk * 8) =
-          *reinterpret_cast<const uint4*>(sO + row * kL2_OUT_PITCH + cchunk * 16);
+          *reinterpret_cast<const uint4*>(sO + row * kL4_OUT_PITCH + cchunk * 16);
   }
 }
 
-static size_t lookup_enc1_v3_smem() { return (size_t)kCorrK * kW1Pitch * 2 + (size_t)kL2_WARPS * kPyr0WarpFloats * 4; }
+template <int D>
+static size_t lookup_enc1_v4_smem() { return (size_t)kL4_WARPS * L4<D>::WARP_BYTES; }
 
 
 // ------------------------------------------------------------------------------------------
@@ -571,11 +644,12 @@ __global__ void __launch_bounds__(256, 1) conv3x3_hmma_kernel(const ConvArgs a) 
       }
     }
     __syncthreads();
-    for (int i = tid; i < 128 * 9; i += 256) {
-      const int pl = i / 9, t = i % 9;
+    for (int k = tid; k < 128 * 9; k += 256) {
+      const int t = k / 128, pl = k % 128, i = pl * 9 + t;     // plane-major: consecutive threads = consecutive pixels of a tap
       const int yy = y0 + pl / TW, xx = x0 + pl % TW;
       if (yy < a.h && xx < a.w)
-        a.s9[((long long)yy * a.w + xx) * 18 + t] = ((sS9[i] + sS9[128 * 9 + i]) + sS9[2 * 128 * 9 + i]) + sS9[3 * 128 * 9 + i];
+        a.s9[s9_index((long long)a.h * a.w, 0, t, (long long)yy * a.w + xx)] =
+            ((sS9[i] + sS9[128 * 9 + i]) + sS9[2 * 128 * 9 + i]) + sS9[3 * 128 * 9 + i];
     }
     return;
   }
@@ -641,8 +715,8 @@ __global__ void __launch_bounds__(256) disp_update_kernel(const float* __restric
   for (int t = 0; t < 9; ++t) {
     const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
     if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-      const float* q = s9 + ((long long)yy * w + xx) * 18 + t;
-      s += (parts == 2) ? __ldg(q) + __ldg(q + 9) : __ldg(q);
+      const float* q = s9 + s9_index(px, 0, t, (long long)yy * w + xx);
+      s += (parts == 2) ? __ldg(q) + __ldg(q + 9 * px) : __ldg(q);
     }
   }
   const float d = h_round(0.01f * h_round(s + __ldg(bd1)));
@@ -692,10 +766,12 @@ int update_configure() {
   if ((rc = configure_conv<256, EPI_DELTA>())) return rc;
   CER_CUDA(cudaFuncSetAttribute(lookup_enc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)lookup_enc1_smem(256)));
-  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)lookup_enc1_v3_smem()));
-  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v3_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)lookup_enc1_v3_smem()));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_v4_smem<64>()));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v4_kernel<44>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)lookup_enc1_v4_smem<44>()));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v4_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CER_CUDA(cudaFuncSetAttribute(lookup_enc1_v4_kernel<44>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return CER_OK;
 }
 
@@ -772,6 +848,28 @@ int update_reset_flags(void* workspace, int iters, int h, int w, cudaStream_t st
   return CER_OK;
 }
 
+// KA: [pending delta] + pyramid lookup + 1x1 corr encoder.  The two cascade widths of the reference (core/raft.py:77-81)
+// take the warp-autonomous kernel; any other D (or CER_LOOKUP=general) the general one.
+static void launch_lookup_enc1(const void* blob, const float* volume, const float* origin, float* disp, const float* s9,
+                               int parts, const float* bd1, int apply_prev, int D, float incre, __half* e1, int h, int w,
+                               cudaStream_t stream) {
+  const BlobLayout L = blob_layout();
+  const char* B = (const char*)blob;
+  const long long px = (long long)h * w;
+  if (lookup_variant() == 2 && (D == 64 || D == 44)) {
+    const int grid = ceil_div(px, kL4_WARPS * 32);
+    if (D == 64)
+      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v4_kernel<64>, grid, kL4_WARPS * 32, lookup_enc1_v4_smem<64>(), stream, volume, origin,
+                     disp, s9, parts, bd1, apply_prev, incre, (const uint4*)(B + L.w1f), e1, h, w);
+    else
+      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v4_kernel<44>, grid, kL4_WARPS * 32, lookup_enc1_v4_smem<44>(), stream, volume, origin,
+                     disp, s9, parts, bd1, apply_prev, incre, (const uint4*)(B + L.w1f), e1, h, w);
+  } else {
+    CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
+                   s9, parts, bd1, apply_prev, D, incre, (const __half*)(B + L.w1), (const float*)(B + L.b1), e1, h, w);
+  }
+}
+
 int update_iteration_fused(const void* blob, void* workspace, void* net, const void* inp, float* disp,
                            const float* volume, const float* origin, int D, float incre, int apply_prev, int iter,
                            int stage, int h, int w, cudaStream_t stream) {
@@ -790,22 +888,8 @@ int update_iteration_fused(const void* blob, void* workspace, void* net, const v
   const bool flags_on = tc && tile_flags() && iter >= 0 && iter < kFlagIters;
   const int n_flag_tiles = flag_tiles(h, w);
   auto F = [&](int k) { return flags_on ? ws.flags + ((size_t)iter * kFlagKernels + k) * n_flag_tiles : (int*)nullptr; };
-  // the two cascade widths of the reference (core/raft.py:77-81) take the warp-autonomous kernel; any other D the general one
-  if (lookup_variant() == 2 && (D == 64 || D == 44)) {
-    const int grid = ceil_div(px, kL2_WARPS * 32);
-    if (D == 64)
-      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v3_kernel<64>, grid, kL2_WARPS * 32, lookup_enc1_v3_smem(), stream, volume, origin,
-                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
-                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
-    else
-      CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_v3_kernel<44>, grid, kL2_WARPS * 32, lookup_enc1_v3_smem(), stream, volume, origin,
-                     disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, incre,
-                     (const __half*)(B + L.w1), (const float*)(B + L.b1), ws.e1, h, w);
-  } else {
-    CER_LAUNCH_PDL(KK_LOOKUP, lookup_enc1_kernel, ceil_div(px, kLE_PIX), 256, lookup_enc1_smem(D), stream, volume, origin, disp,
-               ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre, (const __half*)(B + L.w1),
-               (const float*)(B + L.b1), ws.e1, h, w);
-  }
+  launch_lookup_enc1(blob, volume, origin, disp, ws.s9, tc ? 2 : 1, (const float*)(B + L.bd1[stage]), apply_prev, D, incre,
+                     ws.e1, h, w, stream);
   if (!tc) CER_LAUNCH(KK_DISP_ENC, disp_encode_kernel, ceil_div(px * 8, 256), 256, 0, stream, disp, ws.dn, h, w);
   if ((rc = check_launch("lookup_enc1"))) return rc;
   ConvArgs a{};
@@ -867,6 +951,21 @@ int cer_pack_update_weights(const float* const* w, void* blob_host) {
     for (int n = 0; n < 64; ++n)
       for (int k = 0; k < kCorrPlanes; ++k) d[k * 64 + n] = H(w[0][n * kCorrPlanes + k]);
     memcpy(B + L.b1, w[1], 64 * 4);
+    // the same matrix as mma.sync m16n8k16 B fragments: [k16 block][lane][n8 block][2] words, word r of lane (g, q) =
+    // (w1[kb*16 + 8r + 2q][nb*8 + g], w1[kb*16 + 8r + 2q + 1][nb*8 + g]), with the fp16 bias as row 33
+    uint32_t* f = (uint32_t*)(B + L.w1f);
+    for (int kb = 0; kb < kCorrK / 16; ++kb)
+      for (int lane = 0; lane < 32; ++lane)
+        for (int nb = 0; nb < 8; ++nb)
+          for (int r = 0; r < 2; ++r) {
+            const int k = kb * 16 + 8 * r + 2 * (lane & 3), n = nb * 8 + (lane >> 2);
+            const __half hb = H(w[1][n]);                     // row 33 = bias (the kernel feeds a constant 1 as plane 33)
+            const __half hlo = k == kCorrPlanes ? hb : d[k * 64 + n], hhi = k + 1 == kCorrPlanes ? hb : d[(k + 1) * 64 + n];
+            unsigned short lo, hi;
+            memcpy(&lo, &hlo, 2);
+            memcpy(&hi, &hhi, 2);
+            f[((kb * 32 + lane) * 8 + nb) * 2 + r] = (uint32_t)lo | ((uint32_t)hi << 16);
+          }
   }
   // generic 3x3 OIHW [cout][cin][3][3] slice -> [tap][k][n_total] at column offset n0
   auto pack3x3 = [&](const float* src, int cout, int cin_total, int cin0, int cin_n, __half* dst, int n_total, int n0) {
@@ -965,6 +1064,17 @@ int cer_set_lookup_variant(int variant) {
               "cer_set_lookup_variant: 2 warp-autonomous kernels for the reference configuration (default), 1 general kernels");
   set_lookup_variant(variant);
   return CER_OK;
+}
+
+int cer_lookup_encode(const void* blob, const float* volume, const float* origin, float* disp, int D, float incre, int h,
+                      int w, void* e1, cer_stream_t stream) {
+  CER_REQUIRE(blob && volume && origin && disp && e1, "cer_lookup_encode: null pointer");
+  CER_REQUIRE(h > 0 && w > 0 && D >= 8 && D <= 256, "cer_lookup_encode: bad arguments (8 <= D <= 256)");
+  CER_REQUIRE(aligned16(blob) && aligned16(volume) && aligned16(e1), "cer_lookup_encode: pointers must be 16-byte aligned");
+  int rc;
+  if ((rc = update_configure())) return rc;
+  launch_lookup_enc1(blob, volume, origin, disp, nullptr, 1, nullptr, 0, D, incre, (__half*)e1, h, w, (cudaStream_t)stream);
+  return check_launch("cer_lookup_encode");
 }
 
 int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e, int h,

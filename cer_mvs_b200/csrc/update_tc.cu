@@ -747,10 +747,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             const int mm = quad * 32 + mt * 16 + g + 8 * hf;
             const int y2 = y0 + (mm >> 3), x2 = x0 + (mm & 7);
             if (y2 < a.h && x2 < a.w) {
-              float* dst = a.s9 + (((long long)y2 * a.w + x2) * 2 + chalf) * 9;
-              dst[2 * q4] = d0[mt][2 * hf];
-              dst[2 * q4 + 1] = d0[mt][2 * hf + 1];
-              if (q4 == 0) dst[8] = d1[mt][2 * hf];
+              const long long npx = (long long)a.h * a.w, pp = (long long)y2 * a.w + x2;   // 8 lanes (g) = one 32-byte sector per tap plane
+              a.s9[s9_index(npx, chalf, 2 * q4, pp)] = d0[mt][2 * hf];
+              a.s9[s9_index(npx, chalf, 2 * q4 + 1, pp)] = d0[mt][2 * hf + 1];
+              if (q4 == 0) a.s9[s9_index(npx, chalf, 8, pp)] = d1[mt][2 * hf];
             }
           }
       } else {
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       }
       if (EPI == EPI_DELTA && ok) {   // two partial sums per pixel (one per column half), added by the consumer
 #pragma unroll
-        for (int q = 0; q < 9; ++q) a.s9[(p * 2 + chalf) * 9 + q] = t9[q];
+        for (int q = 0; q < 9; ++q) a.s9[s9_index((long long)a.h * a.w, chalf, q, p)] = t9[q];
       }
       }   // generic (per-pixel) epilogue
       if (a.flags_out != nullptr) {   // this warp's stores of the tile are issued: count it (the publisher thread releases the flag)

@@ -207,6 +207,13 @@ int cer_geometric_filter(const float* depth_ref, const float* K_ref, const float
                          void* mats_ws, unsigned char* masks, float* depth_reprojected, float* x_src, float* y_src,
                          float* rel_diff, unsigned char* geo_mask, float* depth_est, int* n_valid, cer_stream_t stream);
 
+/* CorrBlock.__call__ fused with the first corr-encoder layer (core/corr.py:102-143 + core/update.py:62 `corr_encoder[0:2]`
+ * under autocast): e1[p][0..63] = fp16 relu(conv1x1(lookup(volume, disp)[p])) from the view-mean volume [h*w][D] fp32 of
+ * cer_build_volume, origin [h*w], disp [h*w] fp32; e1 [h*w][64] fp16 NHWC.  The 33 correlation planes never reach HBM.
+ * D = 64 and D = 44 (the reference's cascade widths) take the warp-autonomous kernel, any other D the general one. */
+int cer_lookup_encode(const void* blob, const float* volume, const float* origin, float* disp, int D, float incre, int h,
+                      int w, void* e1, cer_stream_t stream);
+
 /* ConvGRU.forward alone (core/update.py:17-25): net [h*w,64] fp16 NHWC updated in place from
  * inputs inp [h*w,64], dn [h*w,64] (49 disparity-encoder channels + 15 zero), e [h*w,64], all fp16 NHWC. */
 int cer_gru_step(const void* blob, void* workspace, void* net, const void* inp, const void* dn, const void* e,

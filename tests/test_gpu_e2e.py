@@ -148,14 +148,26 @@ def test_dropin_classes_in_reference_loop(golden):
                 corr_frames = corr_fn(disp[:, ii])
                 net, delta = ub(net, inp, disp, corr_frames, stage)
                 disp = disp + delta.float()
+    # the plan on the general lookup kernel does the same arithmetic in the same order -> bit-identical; on its default
+    # (shared-floor taps, tests/test_gpu_lookup_encode.py) it differs by one-ulp fp16 flips of the corr-encoder input
+    from cer_mvs_b200 import _lib
+    try:
+        _lib.check(_lib.lib().cer_set_lookup_variant(1))
+        _, hot_general = _hot(sc, sd, cascade, g, torch.float16)
+    finally:
+        _lib.lib().cer_set_lookup_variant(2)
     _, hot = _hot(sc, sd, cascade, g, torch.float16)
-    assert np.array_equal(disp.cpu().numpy(), hot)            # same kernels, same order -> bit-identical
+    assert np.array_equal(disp.cpu().numpy(), hot_general)
+    r = rel_l1(hot, hot_general)
+    print(f"plan, default lookup kernel vs general: rel L1 {r:.2e}")
+    assert r < 1e-4
     assert rel_l1(disp.cpu().numpy(), g["disp"]) < TOL
 
 
-def test_lookup_kernel_variants_bit_identical(golden, conv_variant):
-    """The warp-autonomous fused lookup kernel (default) and the block-staged one produce the same bits: the
-    three-FMA division of lookup_tap_padded is the correctly rounded quotient, everything else is the same arithmetic."""
+def test_lookup_kernel_variants(golden, conv_variant):
+    """The warp-autonomous fused lookup kernel (default) and the general one through the whole loop: each is bit-identical
+    between graph replay and eager launches; against each other they differ by the shared-floor taps of the default
+    kernel (tests/test_gpu_lookup_encode.py: one-ulp fp16 flips of the corr-encoder input), far inside the parity bar."""
     from cer_mvs_b200 import _lib
     g = golden("e2e_fp32_unscaled_oob")          # large updates: lookups leave the volume on both sides
     sc, sd, cascade = _inputs(g)
@@ -167,6 +179,9 @@ def test_lookup_kernel_variants_bit_identical(golden, conv_variant):
                 _, outs[(v, graph)] = _hot(sc, sd, cascade, g, torch.float16, use_graph=graph)
     finally:
         _lib.lib().cer_set_lookup_variant(2)
-    for k, o in outs.items():
-        assert np.array_equal(o, outs[(1, True)]), k
-    assert np.isfinite(outs[(2, True)]).all()
+    for v in (1, 2):
+        assert np.array_equal(outs[(v, True)], outs[(v, False)]), v
+        assert np.isfinite(outs[(v, True)]).all()
+    r = rel_l1(outs[(2, True)], outs[(1, True)])
+    print(f"lookup variants, whole loop: rel L1 {r:.2e}")
+    assert r < TOL

@@ -5,7 +5,7 @@
 * configs[0] and configs[1] (1184x1600, 10 views, 16+16 iterations, fp16 autocast) against the reference RUN ON
   THIS GPU: its Python from baseline/_ref, its own alt_cuda_corr kernel from oracle/_ref, real
   torch.cuda.amp.autocast (baseline/refrun.py).  Skipped when those git-ignored artefacts did not travel;
-* the reference's own RAFT.forward after cer_mvs_b200.install.install() == DepthHotPath, bit for bit.
+* the reference's own RAFT.forward after cer_mvs_b200.install.install() == DepthHotPath (general lookup kernel), bit for bit.
 
 North-star bar: relative L1 on disparity <= 1e-3; every test prints the number it achieved.
 """
@@ -107,10 +107,21 @@ def test_reference_raft_forward_after_install_is_depth_hot_path():
     finally:
         refrun.restore_reference_classes()
     assert got.dtype == torch.float64 and got.shape == want.shape
+    # the drop-in classes run the general lookup kernel: the plan on that kernel is the same arithmetic, bit for bit; the
+    # plan's default kernel shares floor and weights between the taps of a level (tests/test_gpu_lookup_encode.py)
+    from cer_mvs_b200 import _lib
+    try:
+        _lib.check(_lib.lib().cer_set_lookup_variant(1))
+        hot_general = _ours(H, W, V, sc, sd, net, inp, cascade, torch.float16)
+    finally:
+        _lib.lib().cer_set_lookup_variant(2)
     hot = _ours(H, W, V, sc, sd, net, inp, cascade, torch.float16)
     err = rel_l1(got.cpu().numpy(), want.cpu().numpy())
-    print(f"reference RAFT.forward with the drop-ins installed vs the stock reference: rel L1 = {err:.3e}")
-    assert np.array_equal(got.cpu().numpy().astype(np.float32), hot)
+    gap = rel_l1(hot, hot_general)
+    print(f"reference RAFT.forward with the drop-ins installed vs the stock reference: rel L1 = {err:.3e}; "
+          f"plan default vs general lookup kernel {gap:.2e}")
+    assert np.array_equal(got.cpu().numpy().astype(np.float32), hot_general)
+    assert gap < 1e-4
     assert err < TOL, err
 
 
