@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "lookup_common.cuh"
+#include "tc_common.cuh"
 #include "update_common.cuh"
 
 namespace cer {
@@ -259,8 +260,9 @@ static size_t lookup_enc1_smem(int D) {
 // KA v4 (plan, D = 64 / 44): the same fused step as one wave of warp-autonomous chunks.
 //   * a warp owns 32 consecutive pixels end to end and the kernel has NO block barrier: 5 warps per CTA, 5 CTAs per SM
 //     = 25 resident warps per SM = 3 700 chunks at cfg 2 = exactly one wave on 148 SMs (round 1: 1.25 waves of 4-warp CTAs).
-//   * the level-0 volume rows go global -> shared memory by cp.async (no row registers, no store instructions); row
-//     pitch = 4 (mod 32) words or 12, so a 16-byte load per lane at equal offsets is conflict-free.
+//   * the level-0 volume rows go global -> shared memory asynchronously (D = 44: one bulk copy of the copy engine per
+//     chunk; D = 64: cp.async into a padded pitch): no row registers, no store instructions.  Row pitch = 4 (mod 32)
+//     words or 12, so a 16-byte load per lane at equal offsets is conflict-free.
 //   * ONE shared window per pixel: the 12 aligned 16-byte pieces [f2-5, f2+6] around the level-2 centre hold every value
 //     the 33 taps touch (the level-1 and level-0 windows are nested in it).  Pieces outside the row come from one zero
 //     piece (= grid_sample's zero padding, exact because D % 4 == 0).  Pair sums S and quad sums Q of the pieces are the
@@ -283,7 +285,8 @@ struct L4 {
   static constexpr int PITCH = (D % 32 == 0) ? D + 4 : D;      // floats
   static constexpr int ROW_BYTES = 32 * PITCH * 4;
   static constexpr int ZERO_OFF = ROW_BYTES > kL4_TILE_BYTES ? ROW_BYTES : kL4_TILE_BYTES;
-  static constexpr int WARP_BYTES = ZERO_OFF + 16;
+  static constexpr int BAR_OFF = ZERO_OFF + 16;               // one mbarrier per warp: arrival of the rows
+  static constexpr int WARP_BYTES = BAR_OFF + 16;
   static_assert(D % 4 == 0 && D >= 8 && D <= 64, "16-byte row pieces; one window covers a level-2 row of <= 16 values");
   static_assert(PITCH % 4 == 0 && (PITCH % 32) % 8 == 4, "pitch = 4, 12, 20 or 28 (mod 32) words");
 };
@@ -325,11 +328,25 @@ __global__ void __launch_bounds__(kL4_WARPS * 32, 5) lookup_enc1_v4_kernel(
   const bool live = lane < npix;
   const int p = p0 + (live ? lane : 0);
   const uint32_t rows_s = smem_u32(wbase), zero_s = rows_s + C::ZERO_OFF;
-  if (lane == 0) *reinterpret_cast<float4*>(wbase + C::ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t bar = rows_s + C::BAR_OFF;
+  if (lane == 0) {
+    *reinterpret_cast<float4*>(wbase + C::ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   pdl_wait();     // volume (build kernel), disp / s9 (previous iteration) are produced upstream; e1 is read upstream
 
-  // ---- the chunk's rows: 32 * D contiguous floats, piece f = it * 32 + lane (coalesced) -> row f / NV ----
-  {
+  // ---- the chunk's rows: 32 * D contiguous floats ----
+  // pitch == row (D = 44): ONE bulk copy of the copy engine per chunk.  Padded pitch (D = 64): cp.async, piece
+  // f = it * 32 + lane (coalesced) -> row f / NV.  (One bulk copy per row was measured: the copy instruction takes
+  // uniform registers, so 32 rows become a 32-trip lane loop -- 28 % of the kernel's stall samples.)
+  if (P == D) {
+    if (lane == 0) {
+      mbar_expect_tx(bar, (uint32_t)npix * D * 4);
+      bulk_g2s(rows_s, volume + (long long)p0 * D, (uint32_t)npix * D * 4, bar);
+    }
+  } else {
     const float4* vsrc = reinterpret_cast<const float4*>(volume + (long long)p0 * D);
     const int nvec = npix * NV;
 #pragma unroll
@@ -379,8 +396,12 @@ __global__ void __launch_bounds__(kL4_WARPS * 32, 5) lookup_enc1_v4_kernel(
   const float w01 = xp0 - (float)f0, w00 = ((float)f0 + 1.f) - xp0;
   const int o1 = f1 - 2 * f2, o0 = f0 - 4 * f2;
 
-  cp_async_wait<0>();
-  __syncwarp();
+  if (P == D) {
+    mbar_wait(bar, 0);
+  } else {
+    cp_async_wait<0>();
+    __syncwarp();
+  }
 
   // ---- 33 taps of this lane's pixel -> fp16 A row (registers) ----
   uint32_t arow[kCorrK / 2];
