@@ -467,6 +467,57 @@ def run_ours(args):
                        "in_plan_kernel": lookup_plan_roof}
         del vol, lout
 
+    # ---- the build kernels on their own (cer_build_volume, same features / cameras): stage 0 as in the step, and stage 1
+    # on the scene's TRUE (smooth) disparity map -- what a trained model hands to the second stage.  The step above runs
+    # random-init GRU weights, whose stage-1 input is noise of ~60 hypothesis steps between neighbouring pixels: every
+    # 16x8 tile is incoherent there and takes the gather pass, so the staged kernel's stage-1 time never shows in it. ----
+    if rank == 0 and cfg == "cfg2" and build_roof is not None:
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        feats = torch.empty(Vc + 1, h1, w1, 64, device=dev, dtype=torch.float16)
+        _lib.check(L.cer_nchw_to_nhwc(scene.d_fm.data_ptr(), 1, feats.data_ptr(), 1, Vc + 1, 64, h1, w1, 0.125, st))
+        ii = torch.zeros(Vc, dtype=torch.int32, device=dev)
+        jj = torch.arange(1, Vc + 1, dtype=torch.int32, device=dev)
+        Kq = scene.d_K[0].clone()
+        Kq[:, :2] /= 4
+        Pq = scene.d_poses[0].contiguous()
+        Pij = torch.empty(Vc, 16, device=dev)
+        _lib.check(L.cer_projection_matrices(Pq.data_ptr(), Kq.contiguous().data_ptr(), ii.data_ptr(), jj.data_ptr(), Vc,
+                                             Pij.data_ptr(), st))
+        origin = torch.zeros(h1, w1, device=dev)
+        disp_in = [torch.zeros(h1, w1, device=dev), torch.from_numpy(scene.sc["true_disp"]).to(dev).contiguous()]
+        stages = [(64, 0.0025 / 64, 1), (44, 0.0025 / 320, 0)]
+        coh = {"what": "cer_build_volume alone, event-timed: stage 0 (zero disparity + shift) and stage 1 on the scene's true "
+                       "(smooth) disparity map; 'staged' = default (TMA-staged source boxes + tcgen05, gather pass for "
+                       "incoherent tiles), 'gather' = cer_set_build_variant(1)"}
+        try:
+            for variant, name in ((0, "staged"), (1, "gather")):
+                _lib.check(L.cer_set_build_variant(variant))
+                for sidx, (Dd, inc, shift) in enumerate(stages):
+                    vol = torch.empty(px, Dd, device=dev)
+                    lo = float(torch.tensor(Dd // 2 * inc).float())
+
+                    def run_build():
+                        _lib.check(L.cer_build_volume(feats.data_ptr(), 1, Pij.data_ptr(), ii.data_ptr(), jj.data_ptr(), Vc,
+                                                      disp_in[sidx].data_ptr(), shift, Dd, inc, lo, origin.data_ptr(),
+                                                      vol.data_ptr(), 1.0 / Vc, 0, h1, w1, st), "cer_build_volume")
+                    for _ in range(3):
+                        run_build()
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(10):
+                        run_build()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms_b = e0.elapsed_time(e1) / 10
+                    alg_b = (Vc + 1) * px * 128.0 + 4.0 * px + 4.0 * px * Dd
+                    coh[f"{name}_stage{sidx}_ms"] = ms_b
+                    coh[f"{name}_stage{sidx}_frac"] = alg_b / (ms_b * 1e-3) / 1e9 / pk["hbm"]
+        finally:
+            L.cer_set_build_variant(args.build_variant if args.build_variant is not None else 0)
+        build_roof["coherent"] = coh
+        del feats
+
     # ---- one image sharded over all ranks (NCCL all-reduce of the partial volume per stage), at every N > 1 ----
     sharded = None
     if world > 1 and not sharded_headline and not two_pass:

@@ -166,13 +166,17 @@ __global__ void __launch_bounds__(256) enc_conv1_kernel(const float* __restrict_
 }
 
 // ---- 3x3 convs ------------------------------------------------------------------------------------------------------
+// Persistent: a CTA stages the [9][CIN][COUT] weights once, then walks its tiles (t = blockIdx.x, += gridDim.x) with the
+// halo tile of the NEXT tile in flight (cp.async, two buffers) while the current one is multiplied.  Instance-norm
+// statistics accumulate in registers over all tiles of the CTA and leave as ONE partial per CTA (round-2 first version:
+// one tile per CTA re-staged 18 - 83 KB of weights for a 14 - 26 KB input tile and wrote 3 700 partials per conv).
 template <int CIN, int COUT, int STRIDE>
 struct C3 {
   static constexpr int HW_ = STRIDE * (ETW - 1) + 3, HH_ = STRIDE * (ETH - 1) + 3;     // halo tile
   static constexpr int APITCH = CIN + 8, WPITCH = COUT + 8;                            // halfs
-  static constexpr int A_BYTES = HW_ * HH_ * APITCH * 2;
+  static constexpr int A_BYTES = (HW_ * HH_ * APITCH * 2 + 127) / 128 * 128;
   static constexpr int W_BYTES = 9 * CIN * WPITCH * 2;
-  static constexpr int SMEM = A_BYTES + W_BYTES + 8 * COUT * 2 * 4;
+  static constexpr int SMEM = 2 * A_BYTES + W_BYTES + 8 * COUT * 2 * 4;
 };
 
 template <int CIN, int COUT, int STRIDE>
@@ -182,52 +186,132 @@ __global__ void __launch_bounds__(256) enc_conv3x3_kernel(const __half* __restri
                                                           int oh, int ow, float* __restrict__ stats_part) {
   using S = C3<CIN, COUT, STRIDE>;
   extern __shared__ __align__(128) unsigned char esm[];
-  const uint32_t sA = smem_u32(esm), sW = sA + S::A_BYTES;
-  float* sred = reinterpret_cast<float*>(esm + S::A_BYTES + S::W_BYTES);
+  const uint32_t sA0 = smem_u32(esm), sW = sA0 + 2 * S::A_BYTES;
+  float* sred = reinterpret_cast<float*>(esm + 2 * S::A_BYTES + S::W_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_x = (ow + ETW - 1) / ETW;
-  const int x0 = (blockIdx.x % tiles_x) * ETW, y0 = (blockIdx.x / tiles_x) * ETH;
+  const int tiles_x = (ow + ETW - 1) / ETW, n_tiles = tiles_x * ((oh + ETH - 1) / ETH);
   constexpr int CPP = CIN / 8;              // 16-byte pieces per pixel
-  for (int i = tid; i < S::HW_ * S::HH_ * CPP; i += 256) {
-    const int hp = i / CPP, c = i % CPP;
-    const int yy = STRIDE * y0 - 1 + hp / S::HW_, xx = STRIDE * x0 - 1 + hp % S::HW_;
-    const bool ok = yy >= 0 && yy < ih && xx >= 0 && xx < iw;
-    e_cp_async16(sA + (hp * S::APITCH + c * 8) * 2, in + ((long long)(ok ? yy : 0) * iw + (ok ? xx : 0)) * CIN + c * 8, ok);
+  constexpr int NPIECE = S::HW_ * S::HH_ * CPP, PPT = (NPIECE + 255) / 256;     // pieces of a halo tile, per thread
+  // piece i = tid + 256 * k of every tile: halo pixel (hy, hx), channel piece c -- the same for all tiles of the CTA
+  int p_hy[PPT], p_hx[PPT], p_soff[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int i = tid + 256 * k, hp = i / CPP, c = i % CPP;
+    p_hy[k] = i < NPIECE ? hp / S::HW_ : -100000;       // a piece past the end never passes the bounds test
+    p_hx[k] = hp % S::HW_;
+    p_soff[k] = (hp * S::APITCH + c * 8) * 2 | (c << 24);
   }
+  auto load_tile = [&](int t, int buf) {
+    const int x0 = (t % tiles_x) * ETW, y0 = (t / tiles_x) * ETH;
+    const uint32_t sA = sA0 + buf * S::A_BYTES;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int yy = STRIDE * y0 - 1 + p_hy[k], xx = STRIDE * x0 - 1 + p_hx[k];
+      const bool ok = yy >= 0 && yy < ih && xx >= 0 && xx < iw;
+      const int c = p_soff[k] >> 24;
+      if (p_hy[k] >= 0)
+        e_cp_async16(sA + (p_soff[k] & 0xffffff), in + ((long long)(ok ? yy : 0) * iw + (ok ? xx : 0)) * CIN + c * 8, ok);
+    }
+  };
   constexpr int WPR = COUT / 8;
   for (int i = tid; i < 9 * CIN * WPR; i += 256) {
     const int k = i / WPR, c = i % WPR;
     e_cp_async16(sW + (k * S::WPITCH + c * 8) * 2, wk + (long long)k * COUT + c * 8, true);
   }
+  if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x, 0);
   e_cp_async_commit();
-  e_cp_async_wait_all();
-  __syncthreads();
-  float acc[COUT / 8][4];
-#pragma unroll
-  for (int j = 0; j < COUT / 8; ++j)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+
+  const int g = lane >> 2, q = lane & 3;
   const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lcol = 8 * (lane >> 4);
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int ky = tap / 3, kx = tap % 3;
+  float bs[COUT / 8][2], st[COUT / 8][4];      // bias; running sum / sum of squares of this thread's two channels per n8 block
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j) {
+    bs[j][0] = __ldg(bias + j * 8 + q * 2);
+    bs[j][1] = __ldg(bias + j * 8 + q * 2 + 1);
+    st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int nt = t + gridDim.x;
+    if (nt < n_tiles) load_tile(nt, buf ^ 1);      // (its previous reader finished before the barrier that ended iteration it - 1)
+    e_cp_async_commit();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the group just committed: tile t (and the weights)
+    __syncthreads();
+    const uint32_t sA = sA0 + buf * S::A_BYTES;
+    float acc[COUT / 8][4];
+#pragma unroll
+    for (int j = 0; j < COUT / 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
     // ldmatrix row of this lane: output pixel x = lrow of tile row `warp` -> halo pixel (STRIDE*warp + ky, STRIDE*x + kx)
-    const uint32_t aRow = sA + (((STRIDE * warp + ky) * S::HW_ + STRIDE * lrow + kx) * S::APITCH + lcol) * 2;
-    const uint32_t bRow = sW + ((tap * CIN + lrow) * S::WPITCH + lcol) * 2;
+    const uint32_t aLane = sA + ((STRIDE * warp * S::HW_ + STRIDE * lrow) * S::APITCH + lcol) * 2;
+    const uint32_t bLane = sW + (lrow * S::WPITCH + lcol) * 2;
 #pragma unroll
-    for (int k16 = 0; k16 < CIN / 16; ++k16) {
-      uint32_t a[4];
-      e_ldmatrix_x4(a, aRow + k16 * 32);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const uint32_t aRow = aLane + ((ky * S::HW_ + kx) * S::APITCH) * 2;
+      const uint32_t bRow = bLane + (tap * CIN * S::WPITCH) * 2;
 #pragma unroll
-      for (int jp = 0; jp < COUT / 16; ++jp) {
-        uint32_t b[4];
-        e_ldmatrix_x4_trans(b, bRow + (k16 * 16 * S::WPITCH + jp * 16) * 2);
-        e_mma16816(acc[2 * jp], a, b[0], b[1]);
-        e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+      for (int k16 = 0; k16 < CIN / 16; ++k16) {
+        uint32_t a[4];
+        e_ldmatrix_x4(a, aRow + k16 * 32);
+#pragma unroll
+        for (int jp = 0; jp < COUT / 16; ++jp) {
+          uint32_t b[4];
+          e_ldmatrix_x4_trans(b, bRow + (k16 * 16 * S::WPITCH + jp * 16) * 2);
+          e_mma16816(acc[2 * jp], a, b[0], b[1]);
+          e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+        }
       }
     }
+    // epilogue: acc + bias -> fp16 -> NHWC store; statistics of the ROUNDED values
+    const int x0 = (t % tiles_x) * ETW, y = (t / tiles_x) * ETH + warp;
+    if (y < oh) {
+#pragma unroll
+      for (int j = 0; j < COUT / 8; ++j) {
+        const int n = j * 8 + q * 2;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int x = x0 + g + 8 * half;
+          const __half2 hv = __floats2half2_rn(acc[j][2 * half] + bs[j][0], acc[j][2 * half + 1] + bs[j][1]);
+          if (x < ow) {
+            *reinterpret_cast<__half2*>(out + ((long long)y * ow + x) * COUT + n) = hv;
+            const float2 f = __half22float2(hv);
+            st[j][0] += f.x; st[j][1] += f.x * f.x; st[j][2] += f.y; st[j][3] += f.y * f.y;
+          }
+        }
+      }
+    }
+    __syncthreads();          // every warp is done with buffer `buf`: the next iteration may refill it
   }
-  conv_epilogue<COUT>(acc, bias, out, ow, oh, x0, y0 + warp, lane, warp, stats_part, sred);
+  e_cp_async_wait_all();
+  if (stats_part != nullptr) {
+    // lanes with the same q hold the same channels: sum over the 8 row groups (xor 4, 8, 16), then over the 8 warps in a
+    // fixed order -> one partial per CTA
+#pragma unroll
+    for (int j = 0; j < COUT / 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = st[j][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        st[j][e] = v;
+      }
+      if (g == 0) {
+        float* d = sred + (warp * COUT + j * 8 + q * 2) * 2;
+        d[0] = st[j][0]; d[1] = st[j][1]; d[2] = st[j][2]; d[3] = st[j][3];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < COUT * 2; i += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) v += sred[wq * COUT * 2 + i];
+      stats_part[(long long)blockIdx.x * COUT * 2 + i] = v;
+    }
+  }
 }
 
 // ---- 1x1 convs ------------------------------------------------------------------------------------------------------
@@ -445,14 +529,45 @@ static EncWs enc_carve(void* base, int H, int W) {
   return w;
 }
 
+// CTAs of the persistent 3x3 conv: SM count x resident CTAs per SM (by shared memory), at most one per tile.
+static int enc_sm_count() {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+template <int CIN, int COUT, int STRIDE>
+static int conv3x3_grid(int oh, int ow) {      // call after the shared-memory attribute is set
+  using S = C3<CIN, COUT, STRIDE>;
+  const int tiles = ((ow + ETW - 1) / ETW) * ((oh + ETH - 1) / ETH);
+  static int per_sm_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev = (dev < 0 || dev >= 64) ? 0 : dev;
+  if (per_sm_dev[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, enc_conv3x3_kernel<CIN, COUT, STRIDE>, 256, S::SMEM) != cudaSuccess || n < 1)
+      n = 1;
+    per_sm_dev[dev] = n;
+  }
+  const int g = enc_sm_count() * per_sm_dev[dev];
+  return tiles < g ? tiles : g;
+}
 template <int CIN, int COUT, int STRIDE>
 static int launch_conv3x3(const __half* in, int ih, int iw, const __half* wk, const float* bias, __half* out, int oh, int ow,
-                          float* part, cudaStream_t stream) {
+                          float* part, int* n_part, cudaStream_t stream) {
   using S = C3<CIN, COUT, STRIDE>;
   static std::atomic<unsigned long long> configured{0};
   if (first_time_on_device(configured))
     CER_CUDA(cudaFuncSetAttribute(enc_conv3x3_kernel<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-  const int grid = ((ow + ETW - 1) / ETW) * ((oh + ETH - 1) / ETH);
+  const int grid = conv3x3_grid<CIN, COUT, STRIDE>(oh, ow);
+  *n_part = grid;
   CER_LAUNCH(KK_LAYOUT, (enc_conv3x3_kernel<CIN, COUT, STRIDE>), grid, 256, S::SMEM, stream, in, ih, iw, wk, bias, out, oh, ow,
              part);
   return check_launch("enc_conv3x3");
@@ -573,28 +688,29 @@ int cer_encoder_forward(const void* blob, void* workspace, const float* image, i
   // layer1: two residual blocks @32, stride 1                                        (extractor.py:50-58)
   __half* x = ws.t1;
   __half* spare[3] = {ws.t0, ws.t2, ws.t3};
+  int np = 0;                           // partial-sum records the last conv wrote (persistent convs: one per CTA)
   for (int blk = 0; blk < 2; ++blk) {
     __half *a = spare[0], *b = spare[1], *o = spare[2];
-    if ((rc = launch_conv3x3<32, 32, 1>(x, h2, w2, W16(L.l1_w[2 * blk]), F32(L.l1_b[2 * blk]), a, h2, w2, part, stream))) return rc;
-    if ((rc = launch_norm(a, stats(cta2, 32, p2, 0), nullptr, nullptr, b, p2 * 32, 32, stream))) return rc;
-    if ((rc = launch_conv3x3<32, 32, 1>(b, h2, w2, W16(L.l1_w[2 * blk + 1]), F32(L.l1_b[2 * blk + 1]), a, h2, w2, part, stream))) return rc;
-    if ((rc = launch_norm(a, stats(cta2, 32, p2, 0), x, nullptr, o, p2 * 32, 32, stream))) return rc;
+    if ((rc = launch_conv3x3<32, 32, 1>(x, h2, w2, W16(L.l1_w[2 * blk]), F32(L.l1_b[2 * blk]), a, h2, w2, part, &np, stream))) return rc;
+    if ((rc = launch_norm(a, stats(np, 32, p2, 0), nullptr, nullptr, b, p2 * 32, 32, stream))) return rc;
+    if ((rc = launch_conv3x3<32, 32, 1>(b, h2, w2, W16(L.l1_w[2 * blk + 1]), F32(L.l1_b[2 * blk + 1]), a, h2, w2, part, &np, stream))) return rc;
+    if ((rc = launch_norm(a, stats(np, 32, p2, 0), x, nullptr, o, p2 * 32, 32, stream))) return rc;
     spare[2] = x;
     x = o;
   }
   // layer2.0: 32 -> 64, stride 2, down-sample shortcut
-  if ((rc = launch_conv3x3<32, 64, 2>(x, h2, w2, W16(L.l2a_w[0]), F32(L.l2a_b[0]), ws.u0, h4, w4, part, stream))) return rc;
-  if ((rc = launch_norm(ws.u0, stats(cta4, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
-  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2a_w[1]), F32(L.l2a_b[1]), ws.u0, h4, w4, part, stream))) return rc;
-  const float* s_b = stats(cta4, 64, p4, 0);
+  if ((rc = launch_conv3x3<32, 64, 2>(x, h2, w2, W16(L.l2a_w[0]), F32(L.l2a_b[0]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_norm(ws.u0, stats(np, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2a_w[1]), F32(L.l2a_b[1]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  const float* s_b = stats(np, 64, p4, 0);
   if ((rc = launch_conv1x1<32, 64, 2, 0>(x, h2, w2, W16(L.l2d_w), F32(L.l2d_b), ws.u2, nullptr, nullptr, 1.f, h4, w4, part, stream))) return rc;
   const float* s_d = stats(cta4, 64, p4, 1);
   if ((rc = launch_norm(ws.u0, s_b, ws.u2, in_ ? s_d : nullptr, ws.u3, p4 * 64, 64, stream))) return rc;
   // layer2.1: 64 -> 64
-  if ((rc = launch_conv3x3<64, 64, 1>(ws.u3, h4, w4, W16(L.l2b_w[0]), F32(L.l2b_b[0]), ws.u0, h4, w4, part, stream))) return rc;
-  if ((rc = launch_norm(ws.u0, stats(cta4, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
-  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2b_w[1]), F32(L.l2b_b[1]), ws.u0, h4, w4, part, stream))) return rc;
-  if ((rc = launch_norm(ws.u0, stats(cta4, 64, p4, 0), ws.u3, nullptr, ws.u2, p4 * 64, 64, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1>(ws.u3, h4, w4, W16(L.l2b_w[0]), F32(L.l2b_b[0]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_norm(ws.u0, stats(np, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2b_w[1]), F32(L.l2b_b[1]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_norm(ws.u0, stats(np, 64, p4, 0), ws.u3, nullptr, ws.u2, p4 * 64, 64, stream))) return rc;
   // conv2 (1x1) and the output layouts
   if (out_dim == 64)
     return launch_conv1x1<64, 64, 1, 1>(ws.u2, h4, w4, W16(L.conv2_w), F32(L.conv2_b), (__half*)out_nhwc, nullptr,
