@@ -79,7 +79,8 @@ struct TcCfg {
   // the streamed-weight convs); the pair's halved weight footprint is what makes room for it
   static constexpr bool S3 = MODE == TC_S3;
   static_assert(!S3 || N == 192, "3-tap stages of the 1-CTA form are sized for the gate conv");
-  static constexpr int TPS = (CG2 || S3) ? 3 : 1;
+  // resident weights (N = 64): nothing to wait for between taps, so all nine go out in one run of 36 MMAs
+  static constexpr int TPS = (N == 64 && !CG2) ? 9 : (CG2 || S3) ? 3 : 1;
   static constexpr int NG = 9 / TPS;                          // stages per 64-channel chunk
   static constexpr int NB = RESIDENT ? NG : S3 ? 2 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
   static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
