@@ -87,47 +87,40 @@ def multires_merge(im1, im2, th=0.02):
     return out
 
 
+_PFM_MAGIC = {1: b"Pf", 3: b"PF"}          # channels -> magic (grey / colour)
+
+
 def write_pfm(file, image, scale=1, flipped=False):
-    """utils/frame_utils.py:138-164.  image: float32 H x W (or H x W x 3 / H x W x 1) numpy array or tensor; rows are
-    flipped here unless the caller already did (``disp_to_depth(..., flip_rows=True)``)."""
-    if isinstance(image, torch.Tensor):
-        image = image.detach().cpu().numpy()
-    if image.dtype.name != "float32":
+    """PFM writer with the file layout of utils/frame_utils.py:138-164 (byte-identical files: tests/test_gpu_io.py):
+    magic line, "width height", signed scale whose sign says little-endian, then the rows bottom-up as raw float32.
+    image: float32 [H, W], [H, W, 1] or [H, W, 3] (numpy or tensor).  ``flipped=True``: the rows already are
+    bottom-up (``disp_to_depth(..., flip_rows=True)`` did it on the device)."""
+    arr = image.detach().cpu().numpy() if isinstance(image, torch.Tensor) else np.asarray(image)
+    if arr.dtype != np.float32:
         raise Exception("Image dtype must be float32.")
-    if not flipped:
-        image = np.flipud(image)
-    if len(image.shape) == 3 and image.shape[2] == 3:
-        color = True
-    elif len(image.shape) == 2 or len(image.shape) == 3 and image.shape[2] == 1:
-        color = False
-    else:
+    channels = 1 if arr.ndim == 2 else (arr.shape[2] if arr.ndim == 3 else 0)
+    if channels not in _PFM_MAGIC:
         raise Exception("Image must have H x W x 3, H x W x 1 or H x W dimensions.")
-    endian = image.dtype.byteorder
-    if endian == "<" or endian == "=" and sys.byteorder == "little":
-        scale = -scale
+    rows = arr if flipped else arr[::-1]
+    little = arr.dtype.byteorder == "<" or (arr.dtype.byteorder in "=|" and sys.byteorder == "little")
+    header = b"%s\n%d %d\n%f\n" % (_PFM_MAGIC[channels], arr.shape[1], arr.shape[0], -scale if little else scale)
     with open(file, "wb") as f:
-        f.write(b"PF\n" if color else b"Pf\n")
-        f.write(b"%d %d\n" % (image.shape[1], image.shape[0]))
-        f.write(b"%f\n" % scale)
-        np.ascontiguousarray(image).tofile(f)
+        f.write(header)
+        f.write(np.ascontiguousarray(rows).tobytes())
 
 
 def readPFM(file):
-    """utils/frame_utils.py:10-40: returns the image top-down (float32, H x W or H x W x 3)."""
+    """PFM reader (the inverse of write_pfm; utils/frame_utils.py:10-40): float32 [H, W] or [H, W, 3], rows top-down."""
     with open(file, "rb") as f:
-        header = f.readline().rstrip()
-        if header == b"PF":
-            color = True
-        elif header == b"Pf":
-            color = False
-        else:
+        magic = f.readline().strip()
+        channels = {v: k for k, v in _PFM_MAGIC.items()}.get(magic)
+        if channels is None:
             raise Exception("Not a PFM file.")
-        m = re.match(rb"^(\d+)\s(\d+)\s$", f.readline())
-        if not m:
+        dims = re.fullmatch(rb"(\d+)\s(\d+)\s", f.readline())
+        if dims is None:
             raise Exception("Malformed PFM header.")
-        width, height = map(int, m.groups())
-        scale = float(f.readline().rstrip())
-        endian = "<" if scale < 0 else ">"
-        data = np.fromfile(f, endian + "f")
-    shape = (height, width, 3) if color else (height, width)
-    return np.flipud(np.reshape(data, shape))
+        width, height = int(dims.group(1)), int(dims.group(2))
+        little = float(f.readline().strip()) < 0
+        data = np.frombuffer(f.read(), dtype="<f4" if little else ">f4")
+    shape = (height, width) if channels == 1 else (height, width, 3)
+    return np.ascontiguousarray(data.reshape(shape)[::-1])
