@@ -105,6 +105,9 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[COUT / 8][4], const f
 constexpr int C1_PW = 2 * ETW + 5, C1_PH = 2 * ETH + 5;      // 37 x 21
 constexpr int C1_PITCH = 128;                                // halfs per patch row (111 used + slack for the padded K)
 constexpr int C1_WPITCH = 32 + 8;
+// Persistent like the 3x3 convs: weights staged once per CTA, the next tile's patch values travel in registers while the
+// current tile is multiplied (thread = one (patch row, colour) pair x a run of 10 columns: no per-element index division).
+constexpr int C1_RUN = 10;                                   // columns per thread: 4 threads cover the 37 of a patch row
 __global__ void __launch_bounds__(256) enc_conv1_kernel(const float* __restrict__ img, int H, int W,
                                                         const __half* __restrict__ wk /* [7][32][32] k-major */,
                                                         const float* __restrict__ bias, __half* __restrict__ out, int oh,
@@ -113,56 +116,126 @@ __global__ void __launch_bounds__(256) enc_conv1_kernel(const float* __restrict_
   __shared__ __align__(16) __half sW[7 * 32 * C1_WPITCH];
   __shared__ float sred[8 * 32 * 2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_x = (ow + ETW - 1) / ETW;
-  const int x0 = (blockIdx.x % tiles_x) * ETW, y0 = (blockIdx.x / tiles_x) * ETH;
+  const int tiles_x = (ow + ETW - 1) / ETW, n_tiles = tiles_x * ((oh + ETH - 1) / ETH);
   for (int i = tid; i < 7 * 32 * 4; i += 256) {          // weights: 16-byte pieces
     const int k = i >> 2, c = i & 3;
     *reinterpret_cast<uint4*>(sW + k * C1_WPITCH + c * 8) = __ldg(reinterpret_cast<const uint4*>(wk) + i);
   }
+  for (int i = tid; i < (C1_PH + 1) * C1_PITCH; i += 256) sP[i] = __float2half_rn(0.f);     // slack columns / row stay zero
   const long long plane = (long long)H * W;
-  for (int i = tid; i < (C1_PH + 1) * C1_PITCH; i += 256) {
-    const int r = i / C1_PITCH, e = i % C1_PITCH;
-    float v = 0.f;
-    if (r < C1_PH && e < C1_PW * 3) {
-      const int px_ = e / 3, c = e % 3;
-      const int yy = 2 * y0 - 3 + r, xx = 2 * x0 - 3 + px_;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        v = __ldg(img + c * plane + (long long)yy * W + xx);
+  // this thread's share of a patch: row pr (0..20), colour pc, columns pq*10 .. pq*10+9 (< 37)
+  const int pair = tid >> 2, pq = tid & 3;
+  const int pr = pair / 3, pc = pair % 3;
+  const bool p_on = pair < C1_PH * 3;
+  float pv[C1_RUN];
+  auto fetch = [&](int t) {
+    const int x0 = (t % tiles_x) * ETW, y0 = (t / tiles_x) * ETH;
+    const int yy = 2 * y0 - 3 + pr;
+    const bool row_ok = p_on && yy >= 0 && yy < H;
+    const float* src = img + pc * plane + (long long)(row_ok ? yy : 0) * W;
+#pragma unroll
+    for (int e = 0; e < C1_RUN; ++e) {
+      const int px_ = pq * C1_RUN + e, xx = 2 * x0 - 3 + px_;
+      float v = 0.f;
+      if (row_ok && px_ < C1_PW && xx >= 0 && xx < W) {
+        v = __ldg(src + xx);
         if (normalize) v = __fsub_rn(__fmul_rn(v, (float)(2 / 255.)), 1.f);       // core/raft.py:40-41
       }
+      pv[e] = v;
     }
-    sP[i] = __float2half_rn(v);
-  }
-  __syncthreads();
-  float acc[4][4];
+  };
+  auto stash = [&]() {
+    if (!p_on) return;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    for (int e = 0; e < C1_RUN; ++e) {
+      const int px_ = pq * C1_RUN + e;
+      if (px_ < C1_PW) sP[pr * C1_PITCH + px_ * 3 + pc] = __float2half_rn(pv[e]);
+    }
+  };
   const int g = lane >> 2, q = lane & 3;
+  float bs[4][2], st[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bs[j][0] = __ldg(bias + j * 8 + q * 2);
+    bs[j][1] = __ldg(bias + j * 8 + q * 2 + 1);
+    st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+  }
   const uint32_t bBase = smem_u32(sW) + (((lane & 7) + 8 * ((lane >> 3) & 1)) * C1_WPITCH + 8 * (lane >> 4)) * 2;
+  if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+  __syncthreads();                       // zero fill of sP is complete before the first stash
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    stash();
+    __syncthreads();
+    if (t + (int)gridDim.x < n_tiles) fetch(t + gridDim.x);        // in flight while this tile is multiplied
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
 #pragma unroll 1
-  for (int ky = 0; ky < 7; ++ky) {
-    const __half* prow = sP + (2 * warp + ky) * C1_PITCH;
+    for (int ky = 0; ky < 7; ++ky) {
+      const __half* prow = sP + (2 * warp + ky) * C1_PITCH;
 #pragma unroll
-    for (int k16 = 0; k16 < 2; ++k16) {
-      // A fragment: rows g / g + 8 = output pixels x0 + g / x0 + g + 8 -> patch column 2 * x, i.e. element offset 6 * x
-      const int kk = k16 * 16 + q * 2;
-      uint32_t a[4];
-      a[0] = *reinterpret_cast<const uint32_t*>(prow + 6 * g + kk);
-      a[1] = *reinterpret_cast<const uint32_t*>(prow + 6 * (g + 8) + kk);
-      a[2] = *reinterpret_cast<const uint32_t*>(prow + 6 * g + kk + 8);
-      a[3] = *reinterpret_cast<const uint32_t*>(prow + 6 * (g + 8) + kk + 8);
+      for (int k16 = 0; k16 < 2; ++k16) {
+        // A fragment: rows g / g + 8 = output pixels x0 + g / x0 + g + 8 -> patch column 2 * x, i.e. element offset 6 * x
+        const int kk = k16 * 16 + q * 2;
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(prow + 6 * g + kk);
+        a[1] = *reinterpret_cast<const uint32_t*>(prow + 6 * (g + 8) + kk);
+        a[2] = *reinterpret_cast<const uint32_t*>(prow + 6 * g + kk + 8);
+        a[3] = *reinterpret_cast<const uint32_t*>(prow + 6 * (g + 8) + kk + 8);
 #pragma unroll
-      for (int jp = 0; jp < 2; ++jp) {
-        uint32_t b[4];
-        e_ldmatrix_x4_trans(b, bBase + ((ky * 32 + k16 * 16) * C1_WPITCH + jp * 16) * 2);
-        e_mma16816(acc[2 * jp], a, b[0], b[1]);
-        e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+        for (int jp = 0; jp < 2; ++jp) {
+          uint32_t b[4];
+          e_ldmatrix_x4_trans(b, bBase + ((ky * 32 + k16 * 16) * C1_WPITCH + jp * 16) * 2);
+          e_mma16816(acc[2 * jp], a, b[0], b[1]);
+          e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+        }
       }
     }
+    const int x0 = (t % tiles_x) * ETW, y = (t / tiles_x) * ETH + warp;
+    if (y < oh) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = j * 8 + q * 2;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int x = x0 + g + 8 * half;
+          const __half2 hv = __floats2half2_rn(acc[j][2 * half] + bs[j][0], acc[j][2 * half + 1] + bs[j][1]);
+          if (x < ow) {
+            *reinterpret_cast<__half2*>(out + ((long long)y * ow + x) * 32 + n) = hv;
+            const float2 f = __half22float2(hv);
+            st[j][0] += f.x; st[j][1] += f.x * f.x; st[j][2] += f.y; st[j][3] += f.y * f.y;
+          }
+        }
+      }
+    }
+    __syncthreads();          // every warp is done with the patch: the next stash may overwrite it
   }
-  conv_epilogue<32>(acc, bias, out, ow, oh, x0, y0 + warp, lane, warp, stats_part, sred);
+  if (stats_part != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = st[j][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        st[j][e] = v;
+      }
+      if (g == 0) {
+        float* d = sred + (warp * 32 + j * 8 + q * 2) * 2;
+        d[0] = st[j][0]; d[1] = st[j][1]; d[2] = st[j][2]; d[3] = st[j][3];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * 2; i += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) v += sred[wq * 32 * 2 + i];
+      stats_part[(long long)blockIdx.x * 32 * 2 + i] = v;
+    }
+  }
 }
 
 // ---- 3x3 convs ------------------------------------------------------------------------------------------------------
@@ -681,10 +754,13 @@ int cer_encoder_forward(const void* blob, void* workspace, const float* image, i
     return r ? nullptr : ws.stats[slot];
   };
   // conv1 -> norm1 -> relu                                                           (extractor.py:146-148)
-  CER_LAUNCH(KK_LAYOUT, enc_conv1_kernel, cta2, 256, 0, stream, image, H, W, W16(L.conv1_w), F32(L.conv1_b), ws.t0, h2, w2,
+  int per_sm1 = 0;                       // persistent: as many CTAs as are resident at once
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, enc_conv1_kernel, 256, 0) != cudaSuccess || per_sm1 < 1) per_sm1 = 1;
+  const int grid1 = cta2 < enc_sm_count() * per_sm1 ? cta2 : enc_sm_count() * per_sm1;
+  CER_LAUNCH(KK_LAYOUT, enc_conv1_kernel, grid1, 256, 0, stream, image, H, W, W16(L.conv1_w), F32(L.conv1_b), ws.t0, h2, w2,
              normalize, part);
   if ((rc = check_launch("enc_conv1"))) return rc;
-  if ((rc = launch_norm(ws.t0, stats(cta2, 32, p2, 0), nullptr, nullptr, ws.t1, p2 * 32, 32, stream))) return rc;
+  if ((rc = launch_norm(ws.t0, stats(grid1, 32, p2, 0), nullptr, nullptr, ws.t1, p2 * 32, 32, stream))) return rc;
   // layer1: two residual blocks @32, stride 1                                        (extractor.py:50-58)
   __half* x = ws.t1;
   __half* spare[3] = {ws.t0, ws.t2, ws.t3};
