@@ -243,26 +243,30 @@ __global__ void __launch_bounds__(256) enc_conv1_kernel(const float* __restrict_
 // halo tile of the NEXT tile in flight (cp.async, two buffers) while the current one is multiplied.  Instance-norm
 // statistics accumulate in registers over all tiles of the CTA and leave as ONE partial per CTA (round-2 first version:
 // one tile per CTA re-staged 18 - 83 KB of weights for a 14 - 26 KB input tile and wrote 3 700 partials per conv).
-template <int CIN, int COUT, int STRIDE>
+// RPW = tile rows per warp: the CTA tile is 16 x (8 * RPW) output pixels.  With RPW = 2 a warp multiplies two 16-pixel
+// rows against the same B fragments: 2 A + COUT/16 B ldmatrix per 2 * COUT/8 MMAs instead of 1 + COUT/16 per COUT/8 (the
+// one-row form is bound by shared-memory bandwidth: ncu tensor pipe 41 % active with issue slots half empty).
+template <int CIN, int COUT, int STRIDE, int RPW>
 struct C3 {
-  static constexpr int HW_ = STRIDE * (ETW - 1) + 3, HH_ = STRIDE * (ETH - 1) + 3;     // halo tile
+  static constexpr int TH = ETH * RPW;                                                  // tile rows
+  static constexpr int HW_ = STRIDE * (ETW - 1) + 3, HH_ = STRIDE * (TH - 1) + 3;      // halo tile
   static constexpr int APITCH = CIN + 8, WPITCH = COUT + 8;                            // halfs
   static constexpr int A_BYTES = (HW_ * HH_ * APITCH * 2 + 127) / 128 * 128;
   static constexpr int W_BYTES = 9 * CIN * WPITCH * 2;
   static constexpr int SMEM = 2 * A_BYTES + W_BYTES + 8 * COUT * 2 * 4;
 };
 
-template <int CIN, int COUT, int STRIDE>
-__global__ void __launch_bounds__(256) enc_conv3x3_kernel(const __half* __restrict__ in, int ih, int iw,
+template <int CIN, int COUT, int STRIDE, int RPW>
+__global__ void __launch_bounds__(256, (CIN == 32 && COUT == 32) ? 2 : 1) enc_conv3x3_kernel(const __half* __restrict__ in, int ih, int iw,
                                                           const __half* __restrict__ wk /* [9][CIN][COUT] */,
                                                           const float* __restrict__ bias, __half* __restrict__ out,
                                                           int oh, int ow, float* __restrict__ stats_part) {
-  using S = C3<CIN, COUT, STRIDE>;
+  using S = C3<CIN, COUT, STRIDE, RPW>;
   extern __shared__ __align__(128) unsigned char esm[];
   const uint32_t sA0 = smem_u32(esm), sW = sA0 + 2 * S::A_BYTES;
   float* sred = reinterpret_cast<float*>(esm + 2 * S::A_BYTES + S::W_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_x = (ow + ETW - 1) / ETW, n_tiles = tiles_x * ((oh + ETH - 1) / ETH);
+  const int tiles_x = (ow + ETW - 1) / ETW, n_tiles = tiles_x * ((oh + S::TH - 1) / S::TH);
   constexpr int CPP = CIN / 8;              // 16-byte pieces per pixel
   constexpr int NPIECE = S::HW_ * S::HH_ * CPP, PPT = (NPIECE + 255) / 256;     // pieces of a halo tile, per thread
   // piece i = tid + 256 * k of every tile: halo pixel (hy, hx), channel piece c -- the same for all tiles of the CTA
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(256) enc_conv3x3_kernel(const __half* __restri
     p_soff[k] = (hp * S::APITCH + c * 8) * 2 | (c << 24);
   }
   auto load_tile = [&](int t, int buf) {
-    const int x0 = (t % tiles_x) * ETW, y0 = (t / tiles_x) * ETH;
+    const int x0 = (t % tiles_x) * ETW, y0 = (t / tiles_x) * S::TH;
     const uint32_t sA = sA0 + buf * S::A_BYTES;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
@@ -312,13 +316,15 @@ __global__ void __launch_bounds__(256) enc_conv3x3_kernel(const __half* __restri
     asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the group just committed: tile t (and the weights)
     __syncthreads();
     const uint32_t sA = sA0 + buf * S::A_BYTES;
-    float acc[COUT / 8][4];
+    float acc[RPW][COUT / 8][4];
 #pragma unroll
-    for (int j = 0; j < COUT / 8; ++j)
+    for (int r = 0; r < RPW; ++r)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    // ldmatrix row of this lane: output pixel x = lrow of tile row `warp` -> halo pixel (STRIDE*warp + ky, STRIDE*x + kx)
-    const uint32_t aLane = sA + ((STRIDE * warp * S::HW_ + STRIDE * lrow) * S::APITCH + lcol) * 2;
+      for (int j = 0; j < COUT / 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][j][e] = 0.f;
+    // ldmatrix row of this lane: output pixel x = lrow of tile row RPW*warp + r -> halo pixel (STRIDE*row + ky, STRIDE*x + kx)
+    const uint32_t aLane = sA + ((STRIDE * RPW * warp * S::HW_ + STRIDE * lrow) * S::APITCH + lcol) * 2;
     const uint32_t bLane = sW + (lrow * S::WPITCH + lcol) * 2;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -327,27 +333,34 @@ __global__ void __launch_bounds__(256) enc_conv3x3_kernel(const __half* __restri
       const uint32_t bRow = bLane + (tap * CIN * S::WPITCH) * 2;
 #pragma unroll
       for (int k16 = 0; k16 < CIN / 16; ++k16) {
-        uint32_t a[4];
-        e_ldmatrix_x4(a, aRow + k16 * 32);
+        uint32_t a[RPW][4];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) e_ldmatrix_x4(a[r], aRow + (r * STRIDE * S::HW_ * S::APITCH) * 2 + k16 * 32);
 #pragma unroll
         for (int jp = 0; jp < COUT / 16; ++jp) {
           uint32_t b[4];
           e_ldmatrix_x4_trans(b, bRow + (k16 * 16 * S::WPITCH + jp * 16) * 2);
-          e_mma16816(acc[2 * jp], a, b[0], b[1]);
-          e_mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) {
+            e_mma16816(acc[r][2 * jp], a[r], b[0], b[1]);
+            e_mma16816(acc[r][2 * jp + 1], a[r], b[2], b[3]);
+          }
         }
       }
     }
     // epilogue: acc + bias -> fp16 -> NHWC store; statistics of the ROUNDED values
-    const int x0 = (t % tiles_x) * ETW, y = (t / tiles_x) * ETH + warp;
-    if (y < oh) {
+    const int x0 = (t % tiles_x) * ETW;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int y = (t / tiles_x) * S::TH + RPW * warp + r;
+      if (y >= oh) continue;
 #pragma unroll
       for (int j = 0; j < COUT / 8; ++j) {
         const int n = j * 8 + q * 2;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int x = x0 + g + 8 * half;
-          const __half2 hv = __floats2half2_rn(acc[j][2 * half] + bs[j][0], acc[j][2 * half + 1] + bs[j][1]);
+          const __half2 hv = __floats2half2_rn(acc[r][j][2 * half] + bs[j][0], acc[r][j][2 * half + 1] + bs[j][1]);
           if (x < ow) {
             *reinterpret_cast<__half2*>(out + ((long long)y * ow + x) * COUT + n) = hv;
             const float2 f = __half22float2(hv);
@@ -615,33 +628,33 @@ static int enc_sm_count() {
   }
   return n[dev];
 }
-template <int CIN, int COUT, int STRIDE>
+template <int CIN, int COUT, int STRIDE, int RPW>
 static int conv3x3_grid(int oh, int ow) {      // call after the shared-memory attribute is set
-  using S = C3<CIN, COUT, STRIDE>;
-  const int tiles = ((ow + ETW - 1) / ETW) * ((oh + ETH - 1) / ETH);
+  using S = C3<CIN, COUT, STRIDE, RPW>;
+  const int tiles = ((ow + ETW - 1) / ETW) * ((oh + S::TH - 1) / S::TH);
   static int per_sm_dev[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   dev = (dev < 0 || dev >= 64) ? 0 : dev;
   if (per_sm_dev[dev] == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, enc_conv3x3_kernel<CIN, COUT, STRIDE>, 256, S::SMEM) != cudaSuccess || n < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, enc_conv3x3_kernel<CIN, COUT, STRIDE, RPW>, 256, S::SMEM) != cudaSuccess || n < 1)
       n = 1;
     per_sm_dev[dev] = n;
   }
   const int g = enc_sm_count() * per_sm_dev[dev];
   return tiles < g ? tiles : g;
 }
-template <int CIN, int COUT, int STRIDE>
+template <int CIN, int COUT, int STRIDE, int RPW>
 static int launch_conv3x3(const __half* in, int ih, int iw, const __half* wk, const float* bias, __half* out, int oh, int ow,
                           float* part, int* n_part, cudaStream_t stream) {
-  using S = C3<CIN, COUT, STRIDE>;
+  using S = C3<CIN, COUT, STRIDE, RPW>;
   static std::atomic<unsigned long long> configured{0};
   if (first_time_on_device(configured))
-    CER_CUDA(cudaFuncSetAttribute(enc_conv3x3_kernel<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-  const int grid = conv3x3_grid<CIN, COUT, STRIDE>(oh, ow);
+    CER_CUDA(cudaFuncSetAttribute(enc_conv3x3_kernel<CIN, COUT, STRIDE, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+  const int grid = conv3x3_grid<CIN, COUT, STRIDE, RPW>(oh, ow);
   *n_part = grid;
-  CER_LAUNCH(KK_LAYOUT, (enc_conv3x3_kernel<CIN, COUT, STRIDE>), grid, 256, S::SMEM, stream, in, ih, iw, wk, bias, out, oh, ow,
+  CER_LAUNCH(KK_LAYOUT, (enc_conv3x3_kernel<CIN, COUT, STRIDE, RPW>), grid, 256, S::SMEM, stream, in, ih, iw, wk, bias, out, oh, ow,
              part);
   return check_launch("enc_conv3x3");
 }
@@ -767,25 +780,25 @@ int cer_encoder_forward(const void* blob, void* workspace, const float* image, i
   int np = 0;                           // partial-sum records the last conv wrote (persistent convs: one per CTA)
   for (int blk = 0; blk < 2; ++blk) {
     __half *a = spare[0], *b = spare[1], *o = spare[2];
-    if ((rc = launch_conv3x3<32, 32, 1>(x, h2, w2, W16(L.l1_w[2 * blk]), F32(L.l1_b[2 * blk]), a, h2, w2, part, &np, stream))) return rc;
+    if ((rc = launch_conv3x3<32, 32, 1, 2>(x, h2, w2, W16(L.l1_w[2 * blk]), F32(L.l1_b[2 * blk]), a, h2, w2, part, &np, stream))) return rc;
     if ((rc = launch_norm(a, stats(np, 32, p2, 0), nullptr, nullptr, b, p2 * 32, 32, stream))) return rc;
-    if ((rc = launch_conv3x3<32, 32, 1>(b, h2, w2, W16(L.l1_w[2 * blk + 1]), F32(L.l1_b[2 * blk + 1]), a, h2, w2, part, &np, stream))) return rc;
+    if ((rc = launch_conv3x3<32, 32, 1, 2>(b, h2, w2, W16(L.l1_w[2 * blk + 1]), F32(L.l1_b[2 * blk + 1]), a, h2, w2, part, &np, stream))) return rc;
     if ((rc = launch_norm(a, stats(np, 32, p2, 0), x, nullptr, o, p2 * 32, 32, stream))) return rc;
     spare[2] = x;
     x = o;
   }
   // layer2.0: 32 -> 64, stride 2, down-sample shortcut
-  if ((rc = launch_conv3x3<32, 64, 2>(x, h2, w2, W16(L.l2a_w[0]), F32(L.l2a_b[0]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_conv3x3<32, 64, 2, 1>(x, h2, w2, W16(L.l2a_w[0]), F32(L.l2a_b[0]), ws.u0, h4, w4, part, &np, stream))) return rc;
   if ((rc = launch_norm(ws.u0, stats(np, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
-  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2a_w[1]), F32(L.l2a_b[1]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1, 1>(ws.u1, h4, w4, W16(L.l2a_w[1]), F32(L.l2a_b[1]), ws.u0, h4, w4, part, &np, stream))) return rc;
   const float* s_b = stats(np, 64, p4, 0);
   if ((rc = launch_conv1x1<32, 64, 2, 0>(x, h2, w2, W16(L.l2d_w), F32(L.l2d_b), ws.u2, nullptr, nullptr, 1.f, h4, w4, part, stream))) return rc;
   const float* s_d = stats(cta4, 64, p4, 1);
   if ((rc = launch_norm(ws.u0, s_b, ws.u2, in_ ? s_d : nullptr, ws.u3, p4 * 64, 64, stream))) return rc;
   // layer2.1: 64 -> 64
-  if ((rc = launch_conv3x3<64, 64, 1>(ws.u3, h4, w4, W16(L.l2b_w[0]), F32(L.l2b_b[0]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1, 1>(ws.u3, h4, w4, W16(L.l2b_w[0]), F32(L.l2b_b[0]), ws.u0, h4, w4, part, &np, stream))) return rc;
   if ((rc = launch_norm(ws.u0, stats(np, 64, p4, 0), nullptr, nullptr, ws.u1, p4 * 64, 64, stream))) return rc;
-  if ((rc = launch_conv3x3<64, 64, 1>(ws.u1, h4, w4, W16(L.l2b_w[1]), F32(L.l2b_b[1]), ws.u0, h4, w4, part, &np, stream))) return rc;
+  if ((rc = launch_conv3x3<64, 64, 1, 1>(ws.u1, h4, w4, W16(L.l2b_w[1]), F32(L.l2b_b[1]), ws.u0, h4, w4, part, &np, stream))) return rc;
   if ((rc = launch_norm(ws.u0, stats(np, 64, p4, 0), ws.u3, nullptr, ws.u2, p4 * 64, 64, stream))) return rc;
   // conv2 (1x1) and the output layouts
   if (out_dim == 64)
