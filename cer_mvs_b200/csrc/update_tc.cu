@@ -63,7 +63,11 @@ constexpr int TC_DT_H = TC_HH + 6, TC_DT_W = TC_HW + 6;   // disparity tile for 
 // barrier wait + one commit per 12 MMAs (1 150 tensor cycles) instead of per 4 -- its per-step cost (~500 cycles of waits,
 // fences and commits around 384 cycles of MMA work) is what the role profile shows on the gate conv.  N = 192 only
 // (two 3-tap stages of the N = 256 conv do not fit in shared memory).
-enum TcMode { TC_SINGLE = 0, TC_CG2 = 1, TC_MC2 = 2, TC_MT2 = 3, TC_S3 = 4 };
+// HALF (delta conv): CTAs come in (even, odd) pairs that are NOT a cluster: both walk the same tiles, each computes half
+// of the 256 output channels (template N = 128) with ITS half of the weights resident in shared memory (9 x 16 KB), so a
+// tile costs one run of 36 M128 x N128 MMAs and nothing is streamed (the 1-CTA N = 256 form pulls 295 KB of weights per
+// tile through L2 and pays a barrier wait + commit per 4 MMAs: 790 cycles of issue for 512 cycles of tensor work).
+enum TcMode { TC_SINGLE = 0, TC_CG2 = 1, TC_MC2 = 2, TC_MT2 = 3, TC_S3 = 4, TC_HALF = 5 };
 
 template <int N, int MODE = TC_SINGLE>
 struct TcCfg {
@@ -73,14 +77,16 @@ struct TcCfg {
   // all 9 weight tiles stay in smem: the N = 64 convs, and the delta conv (N = 256) as a CTA pair -- each CTA's half of
   // its 288 KB weight set is 144 KB, exactly the three 3-tap stages the pair form has room for, so the pair never
   // re-streams weights (the 1-CTA form pulls 295 KB per 128-pixel tile through its L2 port for only 36 MMAs)
-  static constexpr bool RESIDENT = (N == 64) || (MODE == TC_CG2 && N == 256);
+  static constexpr bool HALF = MODE == TC_HALF;
+  static_assert(!HALF || N == 128, "the half form computes 128 of the delta conv's 256 channels per CTA");
+  static constexpr bool RESIDENT = (N == 64) || (MODE == TC_CG2 && N == 256) || HALF;
   // taps per weight stage: the CTA-pair form moves a whole kernel row (3 taps) per stage so that the issuing thread
   // pays one barrier wait + one commit per 12 MMAs instead of per 4 (its per-step cost, not the tensor pipe, bounds
   // the streamed-weight convs); the pair's halved weight footprint is what makes room for it
   static constexpr bool S3 = MODE == TC_S3;
   static_assert(!S3 || N == 192, "3-tap stages of the 1-CTA form are sized for the gate conv");
   // resident weights (N = 64): nothing to wait for between taps, so all nine go out in one run of 36 MMAs
-  static constexpr int TPS = (N == 64 && !CG2) ? 9 : (CG2 || S3) ? 3 : 1;
+  static constexpr int TPS = ((N == 64 && !CG2) || HALF) ? 9 : (CG2 || S3) ? 3 : 1;
   static constexpr int NG = 9 / TPS;                          // stages per 64-channel chunk
   static constexpr int NB = RESIDENT ? NG : S3 ? 2 : (CG2 ? (N == 256 ? 3 : 4) : (MT == 2 ? (N == 256 ? 3 : 5) : ((N == 256) ? 4 : 6)));
   static constexpr int NLOC = CG2 ? N / 2 : N;                // weight rows held by this CTA
@@ -93,7 +99,9 @@ struct TcCfg {
   static constexpr int TMEM_COLS = (NACC * MT * N <= 128) ? 128 : (NACC * MT * N <= 256 ? 256 : 512);
   static constexpr int OFF_B = NA * TC_A_BYTES;
   static constexpr int OFF_EXTRA = OFF_B + NB * STAGE_BYTES;                  // DELTA: bias [256] f32 + w2 [9][256] f16; GATES: disparity tile
-  static constexpr int EXTRA_BYTES = (N == 256) ? 256 * 4 + 9 * (256 + 8) * 2 : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
+  // HALF: + the 9 partial dots of 128 pixels handed from the warps of column half 1 to those of column half 0
+  static constexpr int EXTRA_BYTES = (N == 256 || HALF) ? 256 * 4 + 9 * (256 + 8) * 2 + (HALF ? 128 * 9 * 4 : 0)
+                                                       : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
   static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
   static constexpr int NUM_BAR = 2 * NA + 3 * NB + 2 * NACC;  // a_full/empty, b_full/empty/peer_full, acc_full/empty
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
@@ -293,7 +301,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
   // every CTA runs the same number of tile iterations (a CTA pair must stay in lock step); surplus tile indices
   // lie below the image: all loads zero-fill, nothing is stored
   const int n_units = (n_tiles + MT - 1) / MT;                   // a work unit = MT consecutive tiles
-  const int n_iter = (n_units + gridDim.x - 1) / gridDim.x;
+  constexpr bool HALF = C::HALF;
+  const int nhalf = HALF ? (int)(blockIdx.x & 1) : 0;            // which 128 of the 256 output channels
+  const int cta_i = HALF ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cta_n = HALF ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_iter = (n_units + cta_n - 1) / cta_n;
   const int n_src = a.n_src;
   // Every CTA (pair) walks the (chunk, tap) sum in its own rotated order so that the 148 SMs do not all pull the
   // same weight tile out of L2 at the same moment (the accumulation order is free).
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
     // producers then became the critical path of the CTA-pair form.)  The MMA warp issues the generic->async proxy
     // fence after it has observed the barrier.
     for (int it = 0; it < n_iter; ++it) {
-      const int tile0 = (it * gridDim.x + blockIdx.x) * MT;
+      const int tile0 = (it * cta_n + cta_i) * MT;
       for (int cj = 0; cj < n_src * MT; ++cj, ++seq) {
         const int ci = cj / MT, tile = tile0 + cj % MT;          // chunk-major: (chunk 0: tile 0, tile 1), (chunk 1: ...)
         const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
@@ -434,7 +445,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       const int dt = tid - TC_W_DN * 32;
       int seq = 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int tile0 = (it * gridDim.x + blockIdx.x) * MT;
+        const int tile0 = (it * cta_n + cta_i) * MT;
         for (int cj = 0; cj < n_src * MT; ++cj, ++seq) {
           const int ci = cj / MT, tile = tile0 + cj % MT;
           const int st = seq % C::NA;
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             __nanosleep(64);
             if (++spins > (1u << 24)) __trap();
           }
-          const int tile = (t * gridDim.x + blockIdx.x) * MT + j;
+          const int tile = (t * cta_n + cta_i) * MT + j;
           if (tile < n_tiles) st_release_gpu(a.flags_out + tile, 1);
         }
       }
@@ -521,6 +532,12 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             for (int kx = 0; kx < C::TPS; ++kx)
               tma2d_cg2(sB + s * C::STAGE_BYTES + kx * C::B_BYTES, &wmap, 0,
                         ((s * C::TPS + kx) * 2 + (int)rank) * (C::B_BYTES / 256), bar_b_full(s));
+          } else if (HALF) {     // pair layout [tap][half][k-group][128][8]: this CTA's half of every tap is one 16 KB run
+            mbar_expect_tx(bar_b_full(s), C::STAGE_BYTES);
+            const char* w2src = reinterpret_cast<const char*>(a.wtc2);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap)
+              bulk_g2s(sB + tap * C::B_BYTES, w2src + (size_t)(tap * 2 + nhalf) * C::B_BYTES, C::B_BYTES, bar_b_full(s));
           } else {
             mbar_expect_tx(bar_b_full(s), C::STAGE_BYTES);
             bulk_g2s(sB + s * C::STAGE_BYTES, wsrc + (size_t)s * C::STAGE_BYTES, C::STAGE_BYTES, bar_b_full(s));
@@ -672,7 +689,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       const int as = t % C::NACC;
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {
-      const int tile = (t * gridDim.x + blockIdx.x) * MT + j;
+      const int tile = (t * cta_n + cta_i) * MT + j;
       const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
       const int yy = y0 + r, xx = x0 + cc;
       const bool ok = yy < a.h && xx < a.w;
@@ -706,11 +723,12 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 #pragma unroll
           for (int e = 0; e < 4; ++e) d0[mt][e] = d1[mt][e] = 0.f;
 #pragma unroll 2
-        for (int ks = 0; ks < 8; ++ks) {
-          const int c0 = chalf * 128 + ks * 16;
+        for (int ks = 0; ks < N / 32; ++ks) {
+          const int ct = chalf * (N / 2) + ks * 16;        // TMEM column of this CTA's accumulator
+          const int c0 = nhalf * 128 + ct;                 // output channel of the delta.0 conv
           uint32_t r0[8], r1[8];
-          tc_ld_16x256b_x2(lane_addr + c0, r0);
-          tc_ld_16x256b_x2(lane_addr + (16u << 16) + c0, r1);
+          tc_ld_16x256b_x2(lane_addr + ct, r0);
+          tc_ld_16x256b_x2(lane_addr + (16u << 16) + ct, r1);
           const uint32_t b00 = *reinterpret_cast<const uint32_t*>(exw + g * kW2Pitch + c0 + 2 * q4);
           const uint32_t b01 = *reinterpret_cast<const uint32_t*>(exw + g * kW2Pitch + c0 + 8 + 2 * q4);
           const uint32_t b10 = g == 0 ? *reinterpret_cast<const uint32_t*>(exw + 8 * kW2Pitch + c0 + 2 * q4) : 0u;
@@ -741,19 +759,45 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
           arrive_leader(bar_acc_empty(as));           // accumulator stage may be overwritten
         }
         // accumulator fragment (row g / g+8 of m-tile mt, taps 2q, 2q+1; tap 8 in column 0 of the second n-tile)
+        // HALF: this CTA owns part `nhalf` of the delta partials; its two column halves are added here in a fixed order
+        // (warps 4..7 park theirs in shared memory, warps 0..3 add and store), so the consumers still sum two parts.
+        float* sX = reinterpret_cast<float*>(smem + C::OFF_EXTRA + 256 * 4 + 9 * kW2Pitch * 2);      // [128 px][9]
+        if (HALF && chalf == 1) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int mm = quad * 32 + mt * 16 + g + 8 * hf;
-            const int y2 = y0 + (mm >> 3), x2 = x0 + (mm & 7);
-            if (y2 < a.h && x2 < a.w) {
-              const long long npx = (long long)a.h * a.w, pp = (long long)y2 * a.w + x2;   // 8 lanes (g) = one 32-byte sector per tap plane
-              a.s9[s9_index(npx, chalf, 2 * q4, pp)] = d0[mt][2 * hf];
-              a.s9[s9_index(npx, chalf, 2 * q4 + 1, pp)] = d0[mt][2 * hf + 1];
-              if (q4 == 0) a.s9[s9_index(npx, chalf, 8, pp)] = d1[mt][2 * hf];
+            for (int hf = 0; hf < 2; ++hf) {
+              float* d = sX + (quad * 32 + mt * 16 + g + 8 * hf) * 9;
+              d[2 * q4] = d0[mt][2 * hf];
+              d[2 * q4 + 1] = d0[mt][2 * hf + 1];
+              if (q4 == 0) d[8] = d1[mt][2 * hf];
             }
-          }
+        }
+        if (HALF) asm volatile("bar.sync %0, 64;" ::"r"(8 + quad) : "memory");       // the two warps of this lane quadrant
+        if (!HALF || chalf == 0) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int mm = quad * 32 + mt * 16 + g + 8 * hf;
+              const int y2 = y0 + (mm >> 3), x2 = x0 + (mm & 7);
+              float v0 = d0[mt][2 * hf], v1 = d0[mt][2 * hf + 1], v8 = d1[mt][2 * hf];
+              if (HALF) {
+                const float* d = sX + mm * 9;
+                v0 += d[2 * q4];
+                v1 += d[2 * q4 + 1];
+                if (q4 == 0) v8 += d[8];
+              }
+              if (y2 < a.h && x2 < a.w) {
+                const long long npx = (long long)a.h * a.w, pp = (long long)y2 * a.w + x2;   // 8 lanes (g) = one 32-byte sector per tap plane
+                const int part = HALF ? nhalf : chalf;
+                a.s9[s9_index(npx, part, 2 * q4, pp)] = v0;
+                a.s9[s9_index(npx, part, 2 * q4 + 1, pp)] = v1;
+                if (q4 == 0) a.s9[s9_index(npx, part, 8, pp)] = v8;
+              }
+            }
+        }
+        if (HALF) asm volatile("bar.sync %0, 64;" ::"r"(8 + quad) : "memory");       // the parked values have been read
       } else {
 #pragma unroll 1
       for (int cb = chalf * (N / 64); cb < (chalf + 1) * (N / 64); ++cb) {
@@ -904,11 +948,16 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
 // resident half weight sets its M256 x N256 MMAs run at ~200 instead of 128 cycles: 48 us).
 template <int N, int EPI>
 static int tc_configure_one() {
-  CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, TC_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                TcCfg<N, TC_SINGLE>::TOTAL));
-  if (N == 192)
-    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, (N == 192 ? TC_CG2 : TC_SINGLE)>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<N, (N == 192 ? TC_CG2 : TC_SINGLE)>::TOTAL));
+  if constexpr (N == 256) {        // the delta conv only exists as channel halves (TC_HALF)
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128, EPI_DELTA, TC_HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<128, TC_HALF>::TOTAL));
+  } else {
+    CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, TC_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<N, TC_SINGLE>::TOTAL));
+    if constexpr (N == 192)
+      CER_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<N, EPI, TC_CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    TcCfg<N, TC_CG2>::TOTAL));
+  }
   return CER_OK;
 }
 
@@ -1052,14 +1101,26 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
     int rc = make_act_maps(a, &amaps);
     if (rc) return rc;
   }
-  // the gate conv (N = 192) runs as cta_group::2 CTA pairs (79 vs 84 us); every other conv one 128-pixel tile per CTA
-  if (N == 192 && tiles >= 2) return launch_pair<N, EPI, (N == 192 ? TC_CG2 : TC_SINGLE)>(a, tiles, kind, stream);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
   CUtensorMap nomap;
   memset(&nomap, 0, sizeof(nomap));
-  CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, TC_SINGLE>), grid, tc_threads(EPI), (TcCfg<N, TC_SINGLE>::TOTAL), stream, a,
-                 nomap, amaps);
-  return check_launch("conv3x3_tc");
+  if constexpr (N == 256) {
+    // the delta conv as channel halves: CTA 2i / 2i+1 walk the same tiles with one half of the weights resident each
+    // (43.5 -> 40.8 us event-timed, 9.10 -> 8.86 ms per step against one N = 256 tile per CTA with streamed weights)
+    int grid2 = 2 * tiles < kNumSMs ? 2 * tiles : kNumSMs;
+    grid2 &= ~1;
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<128, EPI_DELTA, TC_HALF>), grid2, tc_threads(EPI), (TcCfg<128, TC_HALF>::TOTAL),
+                   stream, a, nomap, amaps);
+    return check_launch("conv3x3_tc");
+  } else {
+    // the gate conv (N = 192) runs as cta_group::2 CTA pairs (79 vs 84 us); the N = 64 convs one 128-pixel tile per CTA
+    if constexpr (N == 192) {
+      if (tiles >= 2) return launch_pair<N, EPI, TC_CG2>(a, tiles, kind, stream);
+    }
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;     // persistent: one CTA per SM
+    CER_LAUNCH_PDL(kind, (conv3x3_tc_kernel<N, EPI, TC_SINGLE>), grid, tc_threads(EPI), (TcCfg<N, TC_SINGLE>::TOTAL), stream, a,
+                   nomap, amaps);
+    return check_launch("conv3x3_tc");
+  }
 }
 
 int launch_conv_tc_dispatch(int n, int epi, const ConvArgs& a, cudaStream_t stream) {

@@ -9,7 +9,7 @@ import torch  # noqa: E402
 from cer_mvs_b200 import _lib, synth  # noqa: E402
 from cer_mvs_b200.hotpath import DepthHotPath  # noqa: E402
 
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 _lib.check(_lib.lib().cer_set_conv_variant(variant))
 H, W, V = 1184, 1600, 2
 sc = synth.make_scene(H, W, V, seed=0)
@@ -26,7 +26,7 @@ for _ in range(2):
     hp(*args)
 torch.cuda.synchronize()
 b = buf.cpu().view(4, 4, 8)
-names = ["corr-enc 3x3 (N=64)", "gates (N=192)", "q/GRU (N=64)", "delta (N=256)"]
+names = ["corr-enc 3x3 (N=64)", "gates (N=192)", "q/GRU (N=64)", "delta (2 x N=128, resident halves)"]
 roles = ["epilogue warp0: wait acc_full", "mma: wait acc_empty / a_full / b_full / issue", "B producer: wait b_empty", "A prod: a_empty / - / - / issue / dn fill / dn wait"]
 print(f"variant {variant}; cycles of CTA 0 (1 cycle ~ 0.52 ns at 1.92 GHz)")
 for k in range(4):
