@@ -722,20 +722,31 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) d0[mt][e] = d1[mt][e] = 0.f;
-#pragma unroll 2
-        for (int ks = 0; ks < N / 32; ++ks) {
+        // All of this warp's accumulator columns come out of TMEM first (N/32 x 2 loads in flight, one wait), and the
+        // accumulator stage goes back to the MMA warp BEFORE the bias / ReLU / delta-head arithmetic: the conv is bound
+        // by this epilogue (role profile: the MMA warp waits 17 % of its time for acc_empty), not by its MMAs.
+        constexpr int NKS = N / 32;
+        uint32_t r0[NKS][8], r1[NKS][8];
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
           const int ct = chalf * (N / 2) + ks * 16;        // TMEM column of this CTA's accumulator
-          const int c0 = nhalf * 128 + ct;                 // output channel of the delta.0 conv
-          uint32_t r0[8], r1[8];
-          tc_ld_16x256b_x2(lane_addr + ct, r0);
-          tc_ld_16x256b_x2(lane_addr + (16u << 16) + ct, r1);
+          tc_ld_16x256b_x2(lane_addr + ct, r0[ks]);
+          tc_ld_16x256b_x2(lane_addr + (16u << 16) + ct, r1[ks]);
+        }
+        tc_ld_wait();
+        if (j == MT - 1) {
+          tc_fence_before();
+          arrive_leader(bar_acc_empty(as));           // accumulator stage may be overwritten
+        }
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          const int c0 = nhalf * 128 + chalf * (N / 2) + ks * 16;      // output channel of the delta.0 conv
           const uint32_t b00 = *reinterpret_cast<const uint32_t*>(exw + g * kW2Pitch + c0 + 2 * q4);
           const uint32_t b01 = *reinterpret_cast<const uint32_t*>(exw + g * kW2Pitch + c0 + 8 + 2 * q4);
           const uint32_t b10 = g == 0 ? *reinterpret_cast<const uint32_t*>(exw + 8 * kW2Pitch + c0 + 2 * q4) : 0u;
           const uint32_t b11 = g == 0 ? *reinterpret_cast<const uint32_t*>(exw + 8 * kW2Pitch + c0 + 8 + 2 * q4) : 0u;
           const float2 bb0 = *reinterpret_cast<const float2*>(exb + c0 + 2 * q4);
           const float2 bb1 = *reinterpret_cast<const float2*>(exb + c0 + 8 + 2 * q4);
-          tc_ld_wait();
           auto frag = [&](const uint32_t (&r)[8], uint32_t (&af)[4]) {
             const __half2 h0 = __hmax2(__floats2half2_rn(__uint_as_float(r[0]) + bb0.x, __uint_as_float(r[1]) + bb0.y), hzero);
             const __half2 h1 = __hmax2(__floats2half2_rn(__uint_as_float(r[2]) + bb0.x, __uint_as_float(r[3]) + bb0.y), hzero);
@@ -747,16 +758,12 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             af[3] = *reinterpret_cast<const uint32_t*>(&h3);
           };
           uint32_t a0[4], a1[4];
-          frag(r0, a0);
-          frag(r1, a1);
+          frag(r0[ks], a0);
+          frag(r1[ks], a1);
           mma16816_f32(d0[0], a0, b00, b01);
           mma16816_f32(d1[0], a0, b10, b11);
           mma16816_f32(d0[1], a1, b00, b01);
           mma16816_f32(d1[1], a1, b10, b11);
-        }
-        if (j == MT - 1) {
-          tc_fence_before();
-          arrive_leader(bar_acc_empty(as));           // accumulator stage may be overwritten
         }
         // accumulator fragment (row g / g+8 of m-tile mt, taps 2q, 2q+1; tap 8 in column 0 of the second n-tile)
         // HALF: this CTA owns part `nhalf` of the delta partials; its two column halves are added here in a fixed order
