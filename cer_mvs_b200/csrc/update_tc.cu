@@ -852,7 +852,8 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
           if (ok) {
             // (prefetching z / net / qx before the accumulator wait was measured slower: 39 vs 36 us -- ptxas holds this
             // kernel at 128 registers, the extra 64 live registers spill, and the loads are L2 hits that the eight
-            // epilogue warps already overlap)
+            // epilogue warps already overlap.  Round 2: a cp.async prefetch one tile ahead into a per-thread shared-memory
+            // slot, no extra registers: 33.9 vs 28.8 us -- sixteen 16-byte copies per thread cost more than they hide.)
             // The element-wise GRU algebra on packed fp16 pairs: autocast rounds every op to fp16, and for fp16 operands
             // HSUB2(1, z) and HMUL2 are exactly fp16(float op) (1 - z and the products are exact in fp32); the final sum
             // is done in fp32 and rounded once, like torch's opmath path.  ~35 % fewer epilogue instructions than the
