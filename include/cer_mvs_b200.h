@@ -158,17 +158,22 @@ int cer_update_step(const void* blob, void* workspace, void* net, const void* in
 
 /* Which tensor-core path the 3x3 convolutions use (A/B switch; every GPU test runs on both):
  *   1 = default (CER_CONV unset): tcgen05.mma + TMEM, persistent CTAs, TMA operand loads; the gate conv (N = 192) as CTA
- *       pairs issuing cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), every other conv one
- *       128-pixel tile per CTA (csrc/update_tc.cu)
+ *       pairs issuing cta_group::2 MMAs (M = 256, each CTA holds half of every weight tile), the delta conv (N = 256) as
+ *       couples of CTAs that each keep one 128-channel half of the weights resident, the N = 64 convs one 128-pixel
+ *       tile per CTA with resident weights (csrc/update_tc.cu)
  *   0 = mma.sync (the v1 kernels, csrc/update_hmma.cu; CER_CONV=hmma).
  * Takes effect for launches and graph captures issued afterwards (a plan that has already captured its graphs keeps
  * the variant it captured). */
 int cer_set_conv_variant(int variant);
 
-/* Which lookup kernels are used (A/B switch; results are bit-identical):
- *   2 = default: warp-autonomous kernels for the reference configuration (radius 5, 3 levels, D = 64 / 44); the plan's
- *       fused lookup + 1x1-encoder kernel keeps only the level-0 rows in shared memory
- *   1 = the general block-staged kernels only (any D <= 1024 / any radius; CER_LOOKUP=general). */
+/* Which lookup kernels are used (A/B switch):
+ *   2 = default: warp-autonomous kernels for the reference configuration (radius 5, 3 levels, D = 64 / 44).  The
+ *       drop-in lookup (cer_lookup) is bit-identical to the general kernel.  The plan's fused lookup + 1x1-encoder kernel
+ *       (cer_lookup_encode) evaluates the reference's normalise / unnormalise round trip once per pyramid level and shares
+ *       floor and weights between the eleven taps of the level: <= 1 ulp of the coordinate per tap position, i.e. rare
+ *       one-ulp flips of its fp16 output against the general kernel (tests/test_gpu_lookup_encode.py)
+ *   1 = the general kernels only: the reference's per-tap arithmetic, any D / radius (CER_LOOKUP=general).  The drop-in
+ *       classes always compute this arithmetic; a plan on variant 1 is bit-identical to them. */
 int cer_set_lookup_variant(int variant);
 
 /* Debug: per-role wait-cycle counters of the tcgen05 convolutions (tools/conv_roles.py). dev_buf: 4 x 32 uint64. */
