@@ -38,6 +38,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 // TMA tensor load of a 4-D box into this CTA's shared memory, completion on this CTA's mbarrier.  Coordinates are signed:
 // elements outside the tensor are written as zeros.
 __device__ __forceinline__ void tma4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {

@@ -102,8 +102,12 @@ struct TcCfg {
   // HALF: + the 9 partial dots of 128 pixels handed from the warps of column half 1 to those of column half 0
   static constexpr int EXTRA_BYTES = (N == 256 || HALF) ? 256 * 4 + 9 * (256 + 8) * 2 + (HALF ? 128 * 9 * 4 : 0)
                                                        : (N == 192 ? TC_DT_H * TC_DT_W * 4 : 0);
-  static constexpr int OFF_BAR = OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
-  static constexpr int NUM_BAR = 2 * NA + 3 * NB + 2 * NACC;  // a_full/empty, b_full/empty/peer_full, acc_full/empty
+  // N = 64: staging tile of the q/GRU epilogue's element-wise operands (z, net: 16 x 8 pixels x 128 B; q's x-part: x 256 B),
+  // written by TMA one tile ahead with the 128-byte swizzle (1024-byte aligned), read conflict-free by thread = pixel
+  static constexpr int OFF_GRU = (OFF_EXTRA + EXTRA_BYTES + 1023) / 1024 * 1024;
+  static constexpr int GRU_BYTES = (N == 64 && MODE == TC_SINGLE) ? 128 * (128 + 128 + 256) : 0;
+  static constexpr int OFF_BAR = GRU_BYTES ? OFF_GRU + GRU_BYTES : OFF_EXTRA + EXTRA_BYTES;                 // 8-byte aligned
+  static constexpr int NUM_BAR = 2 * NA + 3 * NB + 2 * NACC + 2;  // a_full/empty, b_full/empty/peer_full, acc_full/empty, gru_full/empty
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
 };
@@ -291,6 +295,8 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
   auto bar_b_peer = [&](int i) { return sBar + 8 * (2 * C::NA + 2 * C::NB + i); };      // CG2, leader only
   auto bar_acc_full = [&](int i) { return sBar + 8 * (2 * C::NA + 3 * C::NB + i); };
   auto bar_acc_empty = [&](int i) { return sBar + 8 * (2 * C::NA + 3 * C::NB + C::NACC + i); };
+  const uint32_t bar_gru_full = sBar + 8 * (2 * C::NA + 3 * C::NB + 2 * C::NACC), bar_gru_empty = bar_gru_full + 8;
+  constexpr bool GRU_TMA = EPI == EPI_GRUOUT && C::GRU_BYTES > 0;
   const uint32_t rank = (CG2 || MC2) ? cluster_ctarank() : 0u;      // CG2: 0 = leader (issues the MMAs)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM);
 
@@ -325,6 +331,8 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       mbar_init(bar_acc_full(i), kTwoIssuers ? 2 : 1);
       mbar_init(bar_acc_empty(i), CG2 ? 512 : 256);
     }
+    mbar_init(bar_gru_full, 1);
+    mbar_init(bar_gru_empty, 256);
     *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM + 8) = 0u;     // epilogue warps that finished a tile (flags_out)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -574,6 +582,23 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
           }
         }
       }
+      if (GRU_TMA) {
+        // ---- q/GRU conv: this lane is idle once the resident weights are requested; it moves the element-wise operands
+        // of the epilogue (z, net, q's x-part of one 16 x 8 tile = 64 KB) global -> shared memory one tile ahead, so the
+        // epilogue never exposes their latency (round 1: eight epilogue warps in lock step each waited for eight 32-byte
+        // loads per thread, once per tile; prefetching into registers spills, per-thread cp.async costs more than it hides)
+        pdl_wait();                                   // z / qx / net come from the previous kernels of the chain
+        const uint32_t sG = s0 + C::OFF_GRU;
+        for (int t = 0; t < n_iter; ++t) {
+          const int tile = t * cta_n + cta_i;
+          const int x0 = (tile % tiles_x) * TC_TW, y0 = (tile / tiles_x) * TC_TH;
+          pwait(bar_gru_empty, (t & 1) ^ 1, 0);       // every epilogue thread has copied tile t-1's operands to registers
+          mbar_expect_tx(bar_gru_full, (uint32_t)C::GRU_BYTES);
+          tma3d(sG, &amaps.m[1], 0, x0, y0, bar_gru_full);                         // z    [16][8][128 B]
+          tma3d(sG + 128 * 128, &amaps.m[2], 0, x0, y0, bar_gru_full);             // net  [16][8][128 B]
+          tma4d(sG + 2 * 128 * 128, &amaps.m[3], 0, 0, x0, y0, bar_gru_full);      // qx   [16][8][2][128 B]
+        }
+      }
     }
   } else if (warp == TC_W_MMA || (kTwoIssuers && warp == TC_W_MMA2)) {
     // ================= MMA issuers =================
@@ -701,6 +726,39 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
       if (dep_flags && tile < n_tiles) wait_tile_flag(a.flags_in + tile, lane);
       uint4 pre_a[4];
       if (EPI == EPI_GATES && ok) ldg_half32_raw(a.net + p * 64 + chalf * 32, pre_a);   // net slice of this thread's r chunk
+      // q/GRU conv: this thread's operands (pixel m, channels chalf*32..+31) out of the swizzled staging tile, then the
+      // tile goes back to the producer -- before the accumulator wait, so the next tile's loads overlap this tile's math
+      uint4 gz[4], gn[4];
+      float4 gq[8];
+      if (GRU_TMA) {
+        mbar_wait(bar_gru_full, t & 1);
+        const unsigned char* gt = smem + C::OFF_GRU;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ch = ((chalf * 4 + k) ^ (m & 7)) * 16;                    // 128-byte swizzle: chunk ^ (row & 7)
+          gz[k] = *reinterpret_cast<const uint4*>(gt + m * 128 + ch);
+          gn[k] = *reinterpret_cast<const uint4*>(gt + 128 * 128 + m * 128 + ch);
+        }
+        const int qrow = 2 * m + chalf;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          gq[k] = *reinterpret_cast<const float4*>(gt + 2 * 128 * 128 + qrow * 128 + ((k ^ (qrow & 7)) * 16));
+        // The loads must have DELIVERED before the tile is handed back: the arrive does not depend on their registers, the
+        // loads queue behind the tensor core's operand reads (the MMAs of the next tiles saturate the shared-memory port),
+        // and the copy engine overwrites the tile as soon as the last arrival is in.  Fold every loaded word into one value
+        // the arrive is ordered behind.
+        uint32_t sink = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sink ^= gz[k].x ^ gz[k].y ^ gz[k].z ^ gz[k].w ^ gn[k].x ^ gn[k].y ^ gn[k].z ^ gn[k].w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sink ^= __float_as_uint(gq[k].x) ^ __float_as_uint(gq[k].y) ^ __float_as_uint(gq[k].z) ^ __float_as_uint(gq[k].w);
+        // (a conditional store that practically never fires: an empty asm leaves no trace in the PTX and ptxas drops the
+        // whole chain -- measured: the arrive then overtakes loads that queue behind the MMAs' shared-memory reads and
+        // the next tile's copy overwrites what they were about to read)
+        if (sink == 0x5bd1e995u) *reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM + 12) = sink;
+        mbar_arrive(bar_gru_empty);
+      }
       if (j == 0) pwait(bar_acc_full(as), (t / C::NACC) & 1, 0);
       tc_fence_after();
 
@@ -859,9 +917,18 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             // is done in fp32 and rounded once, like torch's opmath path.  ~35 % fewer epilogue instructions than the
             // unpack-to-float version (the q conv is bound by its epilogue's issue slots, not by its MMAs).
             uint4 zk[4], nk[4];
-            ldg_half32_raw(a.z + p * 64 + n0, zk);
-            ldg_half32_raw(a.net + p * 64 + n0, nk);
-            ld_float32_add(a.qx + p * 64 + n0, v);
+            if (GRU_TMA) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { zk[k] = gz[k]; nk[k] = gn[k]; }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                v[4 * k] += gq[k].x; v[4 * k + 1] += gq[k].y; v[4 * k + 2] += gq[k].z; v[4 * k + 3] += gq[k].w;
+              }
+            } else {
+              ldg_half32_raw(a.z + p * 64 + n0, zk);
+              ldg_half32_raw(a.net + p * 64 + n0, nk);
+              ld_float32_add(a.qx + p * 64 + n0, v);
+            }
             const __half2* z2 = reinterpret_cast<const __half2*>(zk);
             const __half2* n2 = reinterpret_cast<const __half2*>(nk);
             const __half2 one2 = __floats2half2_rn(1.f, 1.f);
@@ -1059,6 +1126,42 @@ static int make_act_maps(const ConvArgs& a, TcMaps* out) {
   return CER_OK;
 }
 
+// q/GRU conv: maps of the epilogue's element-wise operands, one 16 x 8-pixel tile per load, 128-byte swizzle
+// (m[1] = z, m[2] = net: fp16 [h][w][64] as (64, w, h); m[3] = q's x-part: fp32 [h][w][64] as (32, 2, w, h))
+static int make_gru_maps(const ConvArgs& a, TcMaps* out) {
+  EncodeTiledFn fn;
+  int rc = get_encode_fn(&fn);
+  if (rc) return rc;
+  const void* src16[2] = {a.z, a.net};
+  for (int i = 0; i < 2; ++i) {
+    const cuuint64_t gdim[3] = {64, (cuuint64_t)a.w, (cuuint64_t)a.h};
+    const cuuint64_t gstride[2] = {128, (cuuint64_t)a.w * 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)TC_TW, (cuuint32_t)TC_TH};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&out->m[1 + i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(src16[i]), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (GRU operand map %d) failed (%d)", i, (int)r);
+      return CER_ERR_INVALID;
+    }
+  }
+  {
+    const cuuint64_t gdim[4] = {32, 2, (cuuint64_t)a.w, (cuuint64_t)a.h};
+    const cuuint64_t gstride[3] = {128, 256, (cuuint64_t)a.w * 256};
+    const cuuint32_t box[4] = {32, 2, (cuuint32_t)TC_TW, (cuuint32_t)TC_TH};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&out->m[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.qx), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (GRU q map) failed (%d)", (int)r);
+      return CER_ERR_INVALID;
+    }
+  }
+  return CER_OK;
+}
+
 template <int N, int EPI, int MODE>
 static int launch_pair(const ConvArgs& a, int tiles, int kind, cudaStream_t stream) {
   CUtensorMap wmap;
@@ -1107,6 +1210,10 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t stream) {
   TcMaps amaps;
   {
     int rc = make_act_maps(a, &amaps);
+    if (rc) return rc;
+  }
+  if constexpr (EPI == EPI_GRUOUT) {
+    int rc = make_gru_maps(a, &amaps);
     if (rc) return rc;
   }
   CUtensorMap nomap;
