@@ -626,7 +626,8 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) conv3x3_tc_kernel(const Co
             pwait(bar_a_full(ast[j]), ((aseq + j) / C::NA) & 1, 1);
             if (CG2) pwait(bar_b_peer(ast[j]), ((aseq + j) / C::NA) & 1, 1);   // the peer CTA's half of the pixel rows
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // producers' cp.async / st.shared -> UMMA reads
+          // generic-proxy writes of the A stage (the dn chunk's st.shared) -> UMMA reads; stages filled by TMA alone need none
+          if (EPI == EPI_GATES) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           for (int ti = 0; ti < C::NG; ++ti, ++bseq) {
             if (kTwoIssuers && (bseq & 1) != mw) continue;         // the other issuer's step
             const int g = C::RESIDENT ? ti : (ti + rot_g) % C::NG;
