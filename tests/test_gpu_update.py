@@ -91,3 +91,24 @@ def test_unsupported_architecture_fails_loudly():
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ub(torch.zeros(1, 1, 64, 8, 8), torch.zeros(1, 1, 64, 8, 8), torch.zeros(1, 1, 8, 8),
            torch.zeros(1, 3, 33, 8, 8), 0)
+
+
+@pytest.mark.parametrize("hw", [(8, 8), (16, 8), (17, 9), (5, 40), (33, 130)])
+@pytest.mark.parametrize("stage", [0, 1])
+def test_update_block_ragged_and_single_tile_grids(hw, stage):
+    """Grids of one 16 x 8 tile, of partial tiles on both borders and of odd tile counts (the delta conv runs as couples of
+    CTAs over the same tiles, the gate conv as CTA pairs): UpdateBlock against the autocast oracle on seeded inputs."""
+    h, w = hw
+    rs = np.random.RandomState(100 + h * w + stage)
+    sd_np = synth.make_update_weights(seed=2, delta_scale=1.0)
+    ub = _ub(sd_np)
+    net = t(np.tanh(rs.standard_normal((1, 1, 64, h, w))).astype(np.float16).astype(np.float32))
+    inp = t(np.maximum(rs.standard_normal((1, 1, 64, h, w)), 0).astype(np.float16).astype(np.float32))
+    disp = t((rs.uniform(0.2, 0.4, (1, 1, h, w))).astype(np.float32))
+    corr = t((rs.standard_normal((1, 2, 33, h, w)) * 0.5).astype(np.float32))
+    with torch.no_grad():
+        n2, d2 = ub(net.cuda().half(), inp.cuda().half(), disp.cuda(), corr.cuda(), stage)
+    wn, wd = O.update_block(O.to_torch_sd(sd_np), net, inp, disp, corr, stage, autocast=True)
+    dn = (n2.float().cpu() - wn).abs()
+    assert float(dn.max()) < 4e-3 and float((dn > 1e-3).float().mean()) < 2e-3
+    assert rel_l1(d2.cpu().numpy(), wd.numpy()) < 2e-3
